@@ -1,0 +1,162 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference (/root/reference) under the
+shims of oracle/ref_harness.py.  Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs (all small, committed):
+  small_pyramid.npz    96x128 uint8 + float32 frames, every level of channel_pyramid for 4 channel configurations
+  small_model.pb       24-stage depth-2 cascade written by the reference's Model.save
+  small_detect.npz     reference Model.detect / predict_on_image outputs for that model (dense + wald thetas)
+  configA_model.pb     BASELINE config A cascade (256 depth-2 stages, wald thetas), written by the reference
+  configA_detect.npz   reference Model.detect on the 640x480 config-A frame: boxes, scores, n_loc, n_weak,
+                       per-level float64 channel sums
+  generic_model.pb     unbalanced / depth-3 trees (generic-topology path) + reference outputs in generic_detect.npz
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_harness  # noqa: E402
+
+wb = ref_harness.import_reference()
+from waldboost import channels as rch  # noqa: E402
+from waldboost.model import Model as RModel  # noqa: E402
+from waldboost.training import DTree as RDTree  # noqa: E402
+
+from waldboost_b200 import synthetic as S  # noqa: E402
+
+
+def ref_trees(trees):
+    return [RDTree([tuple(f) for f in t.feature], t.threshold, t.left, t.right, t.prediction) for t in trees]
+
+
+def ref_model(shape, opts, trees, thetas):
+    M = RModel(shape, opts)
+    for t, th in zip(ref_trees(trees), thetas):
+        M.append(t, float(th))
+    return M
+
+
+def calibrate(M, chns_list, T, keep_total):
+    """wald thetas from the reference's own DTree.predict_on_image over all windows of the given maps."""
+    m, n, _ = M.shape
+    maps, R, Cc = [], [], []
+    for k, X in enumerate(chns_list):
+        u, v, _ = X.shape
+        rs, cs = np.indices((max(u - m, 0), max(v - n, 0)))
+        maps.append(np.full(rs.size, k)); R.append(rs.ravel()); Cc.append(cs.ravel())
+    mp, R, Cc = np.concatenate(maps), np.concatenate(R), np.concatenate(Cc)
+
+    def stage(t, alive):
+        idx = np.arange(mp.size) if alive is None else alive
+        out = np.empty(idx.size, np.float32)
+        for k, X in enumerate(chns_list):
+            sel = mp[idx] == k
+            out[sel] = M.classifier[t].predict_on_image(X, R[idx][sel], Cc[idx][sel])
+        return out
+    return S.calibrate_thetas(stage, T, keep_total)
+
+
+def detect_record(M, image):
+    M.reset()
+    levels = []
+    for chns, scale in M.channels(image):
+        r, c, h = M.predict_on_image(chns)
+        levels.append((r, c, h, scale, chns))
+    M2 = M
+    n_loc, n_weak = M.n_loc, M.n_weak
+    M.reset()
+    dt = M2.detect(image)
+    return levels, dt.get(), dt.get_field("scores"), n_loc, n_weak
+
+
+def main():
+    # ---------------------------------------------------------------- small pyramid fixtures
+    frame = S.synthetic_frame(1000, 96, 128)
+    frame_f = frame.astype(np.float32) + np.random.default_rng(5).random(frame.shape).astype(np.float32)
+    cfgs = {
+        "hist4_s2_sm1": (dict(shrink=2, n_per_oct=4, smooth=1, channels=rch.grad_hist)),
+        "hist4_s1_sm0": (dict(shrink=1, n_per_oct=2, smooth=0, channels=rch.grad_hist)),
+        "mag_s2_sm1": (dict(shrink=2, n_per_oct=3, smooth=1, channels=rch.grad_mag)),
+        "hist6full_s2_sm1": (dict(shrink=2, n_per_oct=2, smooth=1, channels=lambda im: rch.grad_hist(im, 6, True, 2))),
+    }
+    out = {"frame_u8": frame, "frame_f32": frame_f}
+    for name, opts in cfgs.items():
+        for tag, img in (("u8", frame), ("f32", frame_f)):
+            for k, (chns, scale) in enumerate(rch.channel_pyramid(img, opts)):
+                out[f"{name}/{tag}/{k}"] = chns
+                out[f"{name}/{tag}/{k}/scale"] = np.float64(scale)
+    np.savez_compressed(os.path.join(HERE, "small_pyramid.npz"), **out)
+
+    # ---------------------------------------------------------------- small cascade fixtures
+    opts = dict(shrink=2, n_per_oct=4, smooth=1, channels=rch.grad_hist)
+    shape = (12, 12, 4)
+    lv = list(rch.channel_pyramid(frame, opts))
+    lo, hi = S.channel_quantiles(lv[0][0])
+    trees = S.random_trees(shape, 24, 2, lo, hi, seed=7)
+    M = ref_model(shape, opts, trees, [-np.inf] * 24)
+    th = calibrate(M, [lv[0][0], lv[1][0]], 24, 1e-2)
+    M.theta = [float(x) for x in th]
+    M.save(os.path.join(HERE, "small_model.pb"))
+    M = RModel.load(os.path.join(HERE, "small_model.pb"))
+    rec = {}
+    for prof in ("wald", "dense"):
+        if prof == "dense":
+            M.theta = [-np.inf] * 24
+        levels, boxes, scores, n_loc, n_weak = detect_record(M, frame)
+        rec[f"{prof}/boxes"], rec[f"{prof}/scores"] = boxes, scores
+        rec[f"{prof}/n_loc"], rec[f"{prof}/n_weak"] = np.int64(n_loc), np.int64(n_weak)
+        for k, (r, c, h, scale, _) in enumerate(levels):
+            rec[f"{prof}/{k}/r"], rec[f"{prof}/{k}/c"], rec[f"{prof}/{k}/h"] = r.astype(np.int32), c.astype(np.int32), h
+    np.savez_compressed(os.path.join(HERE, "small_detect.npz"), **rec)
+
+    # ---------------------------------------------------------------- generic topologies
+    rng = np.random.default_rng(11)
+    gtrees = S.random_trees(shape, 6, 3, lo, hi, seed=3) + S.random_trees(shape, 6, 1, lo, hi, seed=4)
+    # unbalanced: root -> (leaf, internal -> (leaf, leaf)) in pre-order
+    for _ in range(6):
+        feature = np.zeros((5, 3), np.uint8); threshold = np.full(5, -2, np.float32); pred = np.zeros(5, np.float32)
+        for k in (0, 2):
+            ch = int(rng.integers(0, 4))
+            feature[k] = (rng.integers(0, 12), rng.integers(0, 12), ch)
+            threshold[k] = np.float32(rng.uniform(lo[ch], hi[ch]))
+        pred[[1, 3, 4]] = rng.normal(0, 0.5, 3).astype(np.float32)
+        from waldboost_b200.training import DTree
+        gtrees.append(DTree(feature, threshold, [1, -1, 3, -1, -1], [2, -1, 4, -1, -1], pred))
+    order = rng.permutation(len(gtrees))
+    gtrees = [gtrees[i] for i in order]
+    G = ref_model(shape, opts, gtrees, [-np.inf] * len(gtrees))
+    gth = calibrate(G, [lv[0][0]], len(gtrees), 3e-2)
+    gth[::4] = -np.inf
+    G.theta = [float(x) for x in gth]
+    G.save(os.path.join(HERE, "generic_model.pb"))
+    G = RModel.load(os.path.join(HERE, "generic_model.pb"))
+    levels, boxes, scores, n_loc, n_weak = detect_record(G, frame)
+    np.savez_compressed(os.path.join(HERE, "generic_detect.npz"), boxes=boxes, scores=scores, n_loc=np.int64(n_loc), n_weak=np.int64(n_weak))
+
+    # ---------------------------------------------------------------- BASELINE config A
+    optsA = dict(shrink=2, n_per_oct=8, smooth=1, channels=rch.grad_hist)
+    frameA = S.synthetic_frame(1000, 480, 640)
+    lvA = list(rch.channel_pyramid(frameA, optsA))
+    loA, hiA = S.channel_quantiles(lvA[0][0])
+    treesA = S.random_trees(shape, 256, 2, loA, hiA, seed=7)
+    MA = ref_model(shape, optsA, treesA, [-np.inf] * 256)
+    thA = calibrate(MA, [lvA[0][0]], 256, 1e-4)
+    MA.theta = [float(x) for x in thA]
+    MA.save(os.path.join(HERE, "configA_model.pb"))
+    MA = RModel.load(os.path.join(HERE, "configA_model.pb"))
+    levels, boxes, scores, n_loc, n_weak = detect_record(MA, frameA)
+    np.savez_compressed(os.path.join(HERE, "configA_detect.npz"), boxes=boxes, scores=scores, n_loc=np.int64(n_loc),
+                        n_weak=np.int64(n_weak), level_sums=np.array([c.astype(np.float64).sum() for *_, c in levels]),
+                        level_counts=np.array([r.size for r, *_ in levels]), thr_lo=loA, thr_hi=hiA)
+    print("config A: hits", scores.size, "n_loc", n_loc, "n_weak", n_weak, "eval_cost", n_weak / n_loc)
+
+
+if __name__ == "__main__":
+    main()

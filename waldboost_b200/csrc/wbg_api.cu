@@ -1,0 +1,407 @@
+// libwbg C ABI: handles, pyramid geometry, argument validation.  Kernels live in wbg_pyramid.cu / wbg_cascade.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "wbg_internal.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+void wbg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* wbg_last_error(void) { return g_err; }
+extern "C" int wbg_abi_version(void) { return WBG_ABI_VERSION; }
+
+extern "C" int wbg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
+    // Largest tile whose planar channel patch + window lists fit a budget that keeps >= 2 CTAs per SM.
+    const int budget = 100 * 1024;
+    const int cand[][2] = {{16, 64}, {16, 32}, {8, 32}, {8, 16}, {4, 16}, {2, 16}, {1, 16}};
+    for (auto& c : cand) {
+        int TR = c[0], TC = c[1];
+        int rows = TR + m - 1;
+        int pitch = TC + n - 1;
+        pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are compacted
+        long long plane = (long long)rows * pitch;
+        long long bytes = plane * C * 4 + (long long)CAS_MAX_WIN * (4 + 4) + 256;
+        if (bytes <= budget) {
+            g->TR = TR; g->TC = TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
+            g->smem_bytes = (int)bytes;
+            return true;
+        }
+    }
+    // last resort: one CTA per SM with the smallest tile
+    int TR = 1, TC = 16, rows = m, pitch = TC + n - 1;
+    pitch += (pitch % 2 == 0);
+    long long plane = (long long)rows * pitch;
+    long long bytes = plane * C * 4 + (long long)CAS_MAX_WIN * 8 + 256;
+    if (bytes <= 220 * 1024) {
+        g->TR = TR; g->TC = TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane; g->smem_bytes = (int)bytes;
+        return true;
+    }
+    return false;
+}
+
+static int channels_of(const wbg_channel_opts* o) {
+    switch (o->kind) {
+        case WBG_CH_GRAD_HIST: return o->n_bins;
+        case WBG_CH_GRAD_MAG: return 1;
+        case WBG_CH_GRAD_MAG_HIST: return 1 + o->n_bins;
+        default: return -1;
+    }
+}
+
+extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
+                               int32_t device_tables, wbg_plan** out) {
+    WBG_REQUIRE(out && opts, "wbg_plan_create: null argument");
+    *out = nullptr;
+    WBG_REQUIRE(H >= 1 && W >= 1, "wbg_plan_create: bad image size %dx%d", H, W);
+    WBG_REQUIRE(opts->shrink == 1 || opts->shrink == 2, "Shrink factor must be integer 1 <= shrink <= 2");
+    WBG_REQUIRE(opts->n_per_oct >= 1 && opts->n_per_oct <= 64, "wbg_plan_create: bad n_per_oct %d", opts->n_per_oct);
+    WBG_REQUIRE(opts->kind >= WBG_CH_GRAD_HIST && opts->kind <= WBG_CH_GRAD_MAG_HIST, "wbg_plan_create: unknown channel kind %d", opts->kind);
+    if (opts->kind != WBG_CH_GRAD_MAG)
+        WBG_REQUIRE(opts->n_bins >= 1 && opts->n_bins <= WBG_MAX_BINS, "wbg_plan_create: n_bins must be in 1..%d", WBG_MAX_BINS);
+    if (opts->kind != WBG_CH_GRAD_HIST)
+        WBG_REQUIRE(opts->norm <= WBG_MAX_NORM, "wbg_plan_create: grad_mag norm must be <= %d", WBG_MAX_NORM);
+    WBG_REQUIRE(win_m >= 0 && win_n >= 0 && win_m <= 256 && win_n <= 256, "wbg_plan_create: bad window %dx%d", win_m, win_n);
+
+    wbg_plan* p = new (std::nothrow) wbg_plan();
+    if (!p) { wbg_set_error("out of host memory"); return WBG_ENOMEM; }
+    p->H = H; p->W = W; p->opts = *opts; p->win_m = win_m; p->win_n = win_n;
+    p->C = channels_of(opts);
+    const int shrink = opts->shrink, npo = opts->n_per_oct;
+
+    // channels.py:93-101 -- octave chain; the size test happens before the yield
+    {
+        int h = H, w = W;
+        long long off = 0;
+        // max_levels > 0 (direct channel-function calls): only the octaves those levels read, and octave 0 even
+        // for images under 8 pixels, which channel_pyramid itself would skip
+        const int oct_cap = opts->max_levels > 0 ? (opts->max_levels + npo - 1) / npo : 1 << 30;
+        while ((!(w < 8 || h < 8) || (opts->max_levels > 0 && p->octaves.empty())) && (int)p->octaves.size() < oct_cap) {
+            OctaveInfo o;
+            o.h = h; o.w = w;
+            o.off = p->octaves.empty() ? 0 : off;
+            if (!p->octaves.empty()) off += (long long)wbg_align_up((size_t)h * w, 64);
+            p->octaves.push_back(o);
+            h /= 2; w /= 2;
+        }
+        p->octave_elems = off;
+    }
+    p->geom_ok = (win_m > 0 && win_n > 0) ? wbg_choose_cascade_geom(win_m, win_n, p->C, &p->geom) : false;
+
+    // channels.py:124-131 -- Python double arithmetic: factor = 2**(-1/n); s = factor**i; int((w*s)/shrink)*shrink
+    const double factor = ::pow(2.0, -1.0 / (double)npo);
+    long long chn = 0, win = 0, nloc = 0;
+    int ptile = 0, ctile = 0;
+    for (size_t k = 0; k < p->octaves.size(); ++k) {
+        const int h = p->octaves[k].h, w = p->octaves[k].w;
+        for (int i = 0; i < npo; ++i) {
+            if (opts->max_levels > 0 && (int)p->levels.size() >= opts->max_levels) break;
+            volatile double s = ::pow(factor, (double)i);
+            volatile double ws = (double)w * s, hs = (double)h * s;
+            volatile double wq = ws / (double)shrink, hq = hs / (double)shrink;
+            const int nw = (int)wq * shrink, nh = (int)hq * shrink;
+            wbg_level L;
+            memset(&L, 0, sizeof(L));
+            L.octave = (int)k; L.src_h = h; L.src_w = w; L.nh = nh; L.nw = nw;
+            L.u = nh / shrink; L.v = nw / shrink;
+            // model.py:243 -- np.indices((max(u-m, 0), max(v-n, 0))); a plan without a window has no grid
+            const bool has_win = win_m > 0 && win_n > 0;
+            L.win_rows = (has_win && L.u > win_m) ? L.u - win_m : 0;
+            L.win_cols = (has_win && L.v > win_n) ? L.v - win_n : 0;
+            L.chn_off = chn;
+            L.win_off = win;
+            L.scale = ((double)nw / (double)W) / (double)shrink;
+            const long long nwin = (long long)L.win_rows * L.win_cols;
+            chn += (long long)wbg_align_up((size_t)L.u * L.v * p->C, 4);
+            win += (long long)wbg_align_up((size_t)nwin, 32);
+            nloc += nwin;
+
+            LevelDev D;
+            memset(&D, 0, sizeof(D));
+            D.oct = (int)k; D.src_h = h; D.src_w = w; D.nh = nh; D.nw = nw; D.u = L.u; D.v = L.v;
+            D.identity = (nh == h && nw == w) ? 1 : 0;
+            D.src_off = p->octaves[k].off; D.chn_off = L.chn_off; D.win_off = L.win_off;
+            D.win_rows = L.win_rows; D.win_cols = L.win_cols;
+            D.ptile0 = ptile;
+            D.ptiles_x = (L.v + PYR_TV - 1) / PYR_TV;
+            D.ptiles_y = (L.u + PYR_TU - 1) / PYR_TU;
+            ptile += D.ptiles_x * D.ptiles_y;
+            D.ctile0 = ctile;
+            if (p->geom_ok && nwin > 0) {
+                D.ctiles_x = (L.win_cols + p->geom.TC - 1) / p->geom.TC;
+                D.ctiles_y = (L.win_rows + p->geom.TR - 1) / p->geom.TR;
+                ctile += D.ctiles_x * D.ctiles_y;
+            }
+            D.inv_scale = (float)(1.0 / L.scale);
+            D.zoom_r = nh > 0 ? (double)h / (double)nh : 1.0;
+            D.zoom_c = nw > 0 ? (double)w / (double)nw : 1.0;
+            p->levels.push_back(L);
+            p->dev_levels.push_back(D);
+        }
+    }
+    p->chn_floats = chn; p->windows = win; p->n_loc = nloc; p->ptiles = ptile; p->ctiles = ctile;
+
+    if (device_tables && !p->dev_levels.empty()) {
+        cudaError_t e = cudaGetDevice(&p->device);
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_levels, p->dev_levels.size() * sizeof(LevelDev));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->d_levels, p->dev_levels.data(), p->dev_levels.size() * sizeof(LevelDev), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            wbg_set_error("wbg_plan_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+            cudaGetLastError();
+            if (p->d_levels) cudaFree(p->d_levels);
+            delete p;
+            return WBG_ECUDA;
+        }
+    }
+    *out = p;
+    return WBG_OK;
+}
+
+extern "C" void wbg_plan_destroy(wbg_plan* plan) {
+    if (!plan) return;
+    if (plan->d_levels) cudaFree(plan->d_levels);
+    delete plan;
+}
+
+extern "C" int wbg_plan_get_info(const wbg_plan* plan, wbg_plan_info* info) {
+    WBG_REQUIRE(plan && info, "wbg_plan_get_info: null argument");
+    memset(info, 0, sizeof(*info));
+    info->H = plan->H; info->W = plan->W;
+    info->n_levels = (int)plan->levels.size();
+    info->n_octaves = (int)plan->octaves.size();
+    info->channels = plan->C; info->win_m = plan->win_m; info->win_n = plan->win_n;
+    info->chn_floats = plan->chn_floats; info->octave_elems = plan->octave_elems;
+    info->windows = plan->windows; info->n_loc = plan->n_loc;
+    return WBG_OK;
+}
+
+extern "C" int wbg_plan_get_levels(const wbg_plan* plan, wbg_level* levels, int32_t cap) {
+    WBG_REQUIRE(plan && (levels || cap == 0), "wbg_plan_get_levels: null argument");
+    WBG_REQUIRE(cap >= (int)plan->levels.size(), "wbg_plan_get_levels: capacity %d < %d levels", cap, (int)plan->levels.size());
+    if (!plan->levels.empty()) memcpy(levels, plan->levels.data(), plan->levels.size() * sizeof(wbg_level));
+    return WBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid
+extern "C" size_t wbg_pyramid_workspace_bytes(const wbg_plan* plan, int32_t dtype, int32_t batch) {
+    if (!plan || batch < 1) return 0;
+    const size_t esz = dtype == WBG_F32 ? 4 : 1;
+    // [octaves 1.. of every frame][min/max per (frame, octave)]
+    size_t oct = wbg_align_up((size_t)plan->octave_elems * esz, 256) * (size_t)batch;
+    size_t mm = wbg_align_up((size_t)batch * plan->octaves.size() * 2 * sizeof(float), 256);
+    return oct + mm + 256;
+}
+
+extern "C" int wbg_channel_pyramid(const wbg_plan* plan, const void* img, int32_t dtype, int32_t batch, float* chns,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    WBG_REQUIRE(plan, "wbg_channel_pyramid: null plan");
+    WBG_REQUIRE(plan->d_levels || plan->levels.empty(), "wbg_channel_pyramid: plan was created without device tables");
+    WBG_REQUIRE(dtype == WBG_U8 || dtype == WBG_F32, "wbg_channel_pyramid: unsupported image dtype %d (uint8 and float32 only)", dtype);
+    WBG_REQUIRE(batch >= 1, "wbg_channel_pyramid: batch must be >= 1");
+    if (plan->levels.empty()) return WBG_OK;
+    WBG_REQUIRE(img && chns && workspace, "wbg_channel_pyramid: null buffer");
+    WBG_REQUIRE(workspace_bytes >= wbg_pyramid_workspace_bytes(plan, dtype, batch), "wbg_channel_pyramid: workspace too small");
+    WBG_REQUIRE(((uintptr_t)chns & 15) == 0 && ((uintptr_t)workspace & 255) == 0, "wbg_channel_pyramid: chns must be 16-byte and workspace 256-byte aligned");
+    return wbg_launch_pyramid(plan, img, dtype, batch, chns, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ model
+template <typename T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+    cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" void wbg_model_destroy(wbg_model* m) {
+    if (!m) return;
+    cudaFree(m->d_feature); cudaFree(m->d_threshold); cudaFree(m->d_left); cudaFree(m->d_right);
+    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2);
+    delete m;
+}
+
+extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
+    WBG_REQUIRE(d && out, "wbg_model_create: null argument");
+    *out = nullptr;
+    WBG_REQUIRE(d->win_m >= 1 && d->win_n >= 1 && d->win_m <= 256 && d->win_n <= 256, "wbg_model_create: bad window %dx%d", d->win_m, d->win_n);
+    WBG_REQUIRE(d->channels >= 1 && d->channels <= 255, "wbg_model_create: bad channel count %d", d->channels);
+    WBG_REQUIRE(d->n_stages >= 0, "wbg_model_create: negative stage count");
+    WBG_REQUIRE(d->max_nodes >= 1 && d->max_nodes <= 127, "wbg_model_create: max_nodes must be in 1..127");
+    const int T = d->n_stages, N = d->max_nodes;
+    if (T > 0)
+        WBG_REQUIRE(d->n_nodes && d->feature && d->threshold && d->left && d->right && d->prediction && d->theta, "wbg_model_create: null array");
+
+    CascadeGeom g;
+    WBG_REQUIRE(wbg_choose_cascade_geom(d->win_m, d->win_n, d->channels, &g),
+                "wbg_model_create: window %dx%dx%d does not fit the shared-memory tile", d->win_m, d->win_n, d->channels);
+
+    std::vector<NodeDev> nodes((size_t)T * N);
+    std::vector<StageD2> d2((size_t)T);
+    bool all_d2 = T > 0 && T <= D2_MAX_STAGES;
+    for (int t = 0; t < T; ++t) {
+        const int nn = d->n_nodes[t];
+        WBG_REQUIRE(nn >= 1 && nn <= N, "wbg_model_create: stage %d has %d nodes (max_nodes %d)", t, nn, N);
+        const uint8_t* F = d->feature + (size_t)t * N * 3;
+        const float* TH = d->threshold + (size_t)t * N;
+        const int8_t* Lf = d->left + (size_t)t * N;
+        const int8_t* Rt = d->right + (size_t)t * N;
+        const float* P = d->prediction + (size_t)t * N;
+        for (int k = 0; k < N; ++k) {
+            NodeDev& nd = nodes[(size_t)t * N + k];
+            nd.off = 0; nd.thr = 0.f; nd.left = -1; nd.right = -1; nd.pred = 0.f;
+            if (k >= nn) continue;
+            nd.pred = P[k];
+            if (Lf[k] >= 0) {
+                // training.py:88 visits internal nodes in ascending index order, so children must come later
+                WBG_REQUIRE(Lf[k] > k && Lf[k] < nn && Rt[k] > k && Rt[k] < nn,
+                            "wbg_model_create: stage %d node %d: children (%d, %d) must satisfy node < child < n_nodes", t, k, Lf[k], Rt[k]);
+                WBG_REQUIRE(F[k * 3 + 0] < d->win_m && F[k * 3 + 1] < d->win_n && F[k * 3 + 2] < d->channels,
+                            "wbg_model_create: stage %d node %d: feature (%d, %d, %d) outside window %dx%dx%d", t, k,
+                            F[k * 3 + 0], F[k * 3 + 1], F[k * 3 + 2], d->win_m, d->win_n, d->channels);
+                nd.off = F[k * 3 + 2] * g.plane + F[k * 3 + 0] * g.pitch + F[k * 3 + 1];
+                nd.thr = TH[k];
+                nd.left = Lf[k]; nd.right = Rt[k];
+            }
+        }
+        // canonical depth-2 form: root, two internal children, four leaves
+        bool is_d2 = false;
+        if (all_d2 && Lf[0] >= 0) {
+            const int a = Lf[0], b = Rt[0];
+            if (Lf[a] >= 0 && Lf[b] >= 0) {
+                const int ll = Lf[a], lr = Rt[a], rl = Lf[b], rr = Rt[b];
+                if (Lf[ll] < 0 && Lf[lr] < 0 && Lf[rl] < 0 && Lf[rr] < 0) {
+                    StageD2& s = d2[t];
+                    const NodeDev* nd = &nodes[(size_t)t * N];
+                    s.off0 = nd[0].off; s.thr0 = nd[0].thr;
+                    s.off1 = nd[a].off; s.thr1 = nd[a].thr;
+                    s.off4 = nd[b].off; s.thr4 = nd[b].thr;
+                    s.p2 = nd[ll].pred; s.p3 = nd[lr].pred; s.p5 = nd[rl].pred; s.p6 = nd[rr].pred;
+                    s.theta = d->theta[t]; s.pad_ = 0.f;
+                    is_d2 = true;
+                }
+            }
+        }
+        all_d2 = all_d2 && is_d2;
+    }
+
+    wbg_model* m = new (std::nothrow) wbg_model();
+    if (!m) { wbg_set_error("out of host memory"); return WBG_ENOMEM; }
+    m->m = d->win_m; m->n = d->win_n; m->C = d->channels; m->T = T; m->N = N; m->geom = g; m->all_d2 = all_d2;
+    cudaError_t e = cudaGetDevice(&m->device);
+    if (e == cudaSuccess && T > 0) {
+        const size_t TN = (size_t)T * N;
+        if (e == cudaSuccess) e = upload(&m->d_feature, d->feature, TN * 3);
+        if (e == cudaSuccess) e = upload(&m->d_threshold, d->threshold, TN);
+        if (e == cudaSuccess) e = upload(&m->d_left, d->left, TN);
+        if (e == cudaSuccess) e = upload(&m->d_right, d->right, TN);
+        if (e == cudaSuccess) e = upload(&m->d_prediction, d->prediction, TN);
+        if (e == cudaSuccess) e = upload(&m->d_theta, d->theta, (size_t)T);
+        if (e == cudaSuccess) e = upload(&m->d_nodes, nodes.data(), TN);
+        if (e == cudaSuccess && all_d2) e = upload(&m->d_d2, d2.data(), (size_t)T);
+    }
+    if (e != cudaSuccess) {
+        wbg_set_error("wbg_model_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        wbg_model_destroy(m);
+        return WBG_ECUDA;
+    }
+    *out = m;
+    return WBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cascade
+extern "C" size_t wbg_cascade_workspace_bytes(const wbg_plan* plan, int32_t batch) {
+    if (!plan || batch < 1) return 0;
+    return wbg_cascade_ws_bytes(plan->windows, (int)plan->levels.size(), batch);
+}
+
+static int check_cascade_args(const wbg_model* model, const void* chns, const wbg_hit* hits, int64_t hit_cap,
+                              const void* stats, const void* n_hits, const void* ws) {
+    WBG_REQUIRE(model, "cascade: null model");
+    WBG_REQUIRE(chns && stats && n_hits && ws, "cascade: null buffer");
+    WBG_REQUIRE(hit_cap >= 0 && (hits || hit_cap == 0), "cascade: bad hit buffer");
+    WBG_REQUIRE(((uintptr_t)chns & 15) == 0 && ((uintptr_t)ws & 255) == 0, "cascade: chns must be 16-byte and workspace 256-byte aligned");
+    return WBG_OK;
+}
+
+extern "C" int wbg_cascade_scan(const wbg_model* model, const wbg_plan* plan, const float* chns, int32_t batch,
+                                wbg_hit* hits, int64_t hit_cap, int32_t* level_counts, uint64_t* stats, int64_t* n_hits,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    WBG_REQUIRE(plan, "wbg_cascade_scan: null plan");
+    int rc = check_cascade_args(model, chns, hits, hit_cap, stats, n_hits, workspace);
+    if (rc) return rc;
+    WBG_REQUIRE(level_counts, "wbg_cascade_scan: null level_counts");
+    WBG_REQUIRE(batch >= 1, "wbg_cascade_scan: batch must be >= 1");
+    WBG_REQUIRE(plan->d_levels, "wbg_cascade_scan: plan was created without device tables");
+    // model.py:238 -- assert ch_image == ch_cls
+    WBG_REQUIRE(plan->C == model->C, "Invalid number of channels. Expected %d given %d.", model->C, plan->C);
+    WBG_REQUIRE(plan->win_m == model->m && plan->win_n == model->n, "wbg_cascade_scan: plan window %dx%d != model window %dx%d",
+                plan->win_m, plan->win_n, model->m, model->n);
+    WBG_REQUIRE(workspace_bytes >= wbg_cascade_workspace_bytes(plan, batch), "wbg_cascade_scan: workspace too small");
+    return wbg_launch_cascade(model, plan->d_levels, (int)plan->levels.size(), plan->ctiles, plan->chn_floats, plan->windows,
+                              chns, batch, hits, hit_cap, level_counts, (unsigned long long*)stats, (long long*)n_hits,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// single channel map: a one-level table is written into the head of the workspace
+static void single_level(int u, int v, int m, int n, const CascadeGeom& g, LevelDev* D, long long* windows, int* tiles) {
+    memset(D, 0, sizeof(*D));
+    D->u = u; D->v = v; D->nh = u; D->nw = v;
+    D->win_rows = u > m ? u - m : 0;
+    D->win_cols = v > n ? v - n : 0;
+    const long long nwin = (long long)D->win_rows * D->win_cols;
+    *windows = (long long)wbg_align_up((size_t)nwin, 32);
+    D->ctiles_x = nwin ? (D->win_cols + g.TC - 1) / g.TC : 0;
+    D->ctiles_y = nwin ? (D->win_rows + g.TR - 1) / g.TR : 0;
+    *tiles = D->ctiles_x * D->ctiles_y;
+    D->inv_scale = 1.0f;
+}
+
+extern "C" size_t wbg_predict_workspace_bytes(int32_t u, int32_t v, int32_t win_m, int32_t win_n) {
+    long long rows = u > win_m ? u - win_m : 0, cols = v > win_n ? v - win_n : 0;
+    long long windows = (long long)wbg_align_up((size_t)(rows * cols), 32);
+    return 256 + wbg_cascade_ws_bytes(windows, 1, 1);
+}
+
+__global__ void wbg_store_level_kernel(LevelDev* dst, LevelDev value) { *dst = value; }
+
+extern "C" int wbg_predict_on_image(const wbg_model* model, const float* X, int32_t u, int32_t v, wbg_hit* hits,
+                                    int64_t hit_cap, uint64_t* stats, int64_t* n_hits, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    int rc = check_cascade_args(model, X, hits, hit_cap, stats, n_hits, workspace);
+    if (rc) return rc;
+    WBG_REQUIRE(u >= 0 && v >= 0, "wbg_predict_on_image: bad map size");
+    WBG_REQUIRE(workspace_bytes >= wbg_predict_workspace_bytes(u, v, model->m, model->n), "wbg_predict_on_image: workspace too small");
+    LevelDev D;
+    long long windows;
+    int tiles;
+    single_level(u, v, model->m, model->n, model->geom, &D, &windows, &tiles);
+    LevelDev* d_level = (LevelDev*)workspace;
+    wbg_store_level_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_level, D);
+    WBG_CUDA_TRY(cudaGetLastError());
+    int32_t* level_counts = (int32_t*)((char*)workspace + 192);
+    return wbg_launch_cascade(model, d_level, 1, tiles, (long long)u * v * model->C, windows, X, 1, hits, hit_cap,
+                              level_counts, (unsigned long long*)stats, (long long*)n_hits, (char*)workspace + 256,
+                              workspace_bytes - 256, (cudaStream_t)stream);
+}

@@ -1,0 +1,498 @@
+// Dense sliding-window WaldBoost cascade for sm_100a.
+//
+// Replaces Model.predict_on_image (reference waldboost/model.py:216-259), DTree.predict_on_image
+// (waldboost/training.py:84-96) and Model.get_boxes (waldboost/model.py:136-147) for every level of every frame
+// of a batch in one launch family:
+//
+//   cascade_kernel   one CTA per tile of TR x TC windows.  The (TR+m-1) x (TC+n-1) x C channel patch is staged
+//                    once in shared memory, channel-planar, so that the 32 lanes of a warp (adjacent windows)
+//                    gather adjacent words.  Windows are scored stage by stage in float32 (stage order, like
+//                    `hs += weak.predict_on_image`), rejected with `hs >= theta[t]`, and the surviving windows of
+//                    the CTA are re-packed (ballot + prefix sum, order preserving) after every stage block so
+//                    early exit does not leave idle lanes.  Survivors set a bit in a per-frame window mask and
+//                    store their score in a dense score map.
+//   mask_*/emit_hits popcount prefix sums over the mask give every survivor its rank in the reference's output
+//                    order (frame, level, r, c) -- the stable boolean filtering of model.py:255-258 -- without a
+//                    sort; boxes are produced in the same pass.
+//
+// No tensor cores: nothing here is a contraction.  The stage loop is bound by shared-memory gathers and issue
+// slots; HBM traffic is one read of the channel pyramid.
+#include <math_constants.h>
+
+#include "wbg_internal.h"
+
+__constant__ StageD2 c_d2[D2_MAX_STAGES];
+
+struct CascadeParams {
+    const float* chns;
+    long long chn_stride;
+    const LevelDev* levels;
+    int n_levels, tiles_per_frame;
+    const NodeDev* nodes;
+    const float* theta;
+    int N, T;
+    int C, m, n;
+    int TR, TC, pitch, plane;
+    unsigned* mask;
+    long long mask_stride;  // words per frame
+    float* score;
+    long long score_stride;  // window slots per frame
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ NodeDev load_node(const NodeDev* p) {
+    int4 r = __ldg(reinterpret_cast<const int4*>(p));
+    NodeDev n;
+    n.off = r.x;
+    n.thr = __int_as_float(r.y);
+    n.left = (short)(r.z & 0xffff);
+    n.right = (short)((unsigned)r.z >> 16);
+    n.pred = __int_as_float(r.w);
+    return n;
+}
+
+__device__ __forceinline__ int find_level_by_ctile(const LevelDev* levels, int n_levels, int tile_id) {
+    int lo = 0, hi = n_levels - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (levels[mid].ctile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <bool D2>
+__global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    float* s_score = tile + ((p.C * p.plane + 3) & ~3);
+    unsigned short* s_woff = reinterpret_cast<unsigned short*>(s_score + CAS_MAX_WIN);
+    __shared__ int s_tot[CAS_WPT * (CAS_THREADS / 32)];
+    __shared__ int s_nact;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    const int lvl = find_level_by_ctile(p.levels, p.n_levels, tile_id);
+    const LevelDev* __restrict__ L = p.levels + lvl;
+    const int v = L->v, win_rows = L->win_rows, win_cols = L->win_cols, ctiles_x = L->ctiles_x;
+    const long long chn_off = L->chn_off, win_off = L->win_off;
+    const int local = tile_id - L->ctile0;
+    const int ty = local / ctiles_x, tx = local - ty * ctiles_x;
+    const int r0 = ty * p.TR, c0 = tx * p.TC;
+    const int rows_valid = min(p.TR, win_rows - r0), cols_valid = min(p.TC, win_cols - c0);
+    const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;
+    const int pitch = p.pitch, plane = p.plane;
+
+    // ---- stage the channel patch, HWC in HBM -> planar in shared memory
+    const float* __restrict__ src = p.chns + (long long)frame * p.chn_stride + chn_off + ((long long)r0 * v + c0) * p.C;
+    if (p.C == 4) {
+        for (int i = tid; i < lrows * lcols; i += CAS_THREADS) {
+            const int rr = i / lcols, cc = i - rr * lcols;
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * v + cc) * 4));
+            float* d = tile + rr * pitch + cc;
+            d[0] = x.x; d[plane] = x.y; d[2 * plane] = x.z; d[3 * plane] = x.w;
+        }
+    } else {
+        for (int i = tid; i < lrows * lcols; i += CAS_THREADS) {
+            const int rr = i / lcols, cc = i - rr * lcols;
+            const float* s = src + ((long long)rr * v + cc) * p.C;
+            float* d = tile + rr * pitch + cc;
+            for (int ch = 0; ch < p.C; ++ch) d[ch * plane] = __ldg(s + ch);
+        }
+    }
+    // ---- all windows of the tile start alive with score 0 (model.py:243-247), row-major
+    const int nwin = rows_valid * cols_valid;
+    for (int i = tid; i < nwin; i += CAS_THREADS) {
+        const int lr = i / cols_valid, lc = i - lr * cols_valid;
+        s_woff[i] = (unsigned short)(lr * pitch + lc);
+        s_score[i] = 0.f;
+    }
+    __syncthreads();
+
+    int n_act = nwin, t = 0;
+    unsigned my_weak = 0;
+    while (t < p.T && n_act > 0) {
+        // stage blocks 1,1,2,4,8,16 then 32 stages: real cascades reject most windows in the first stages
+        const int t_end = min(p.T, t < 1 ? 1 : (t < 32 ? 2 * t : t + 32));
+        int woff[CAS_WPT];
+        float hs[CAS_WPT];
+        bool alive[CAS_WPT];
+#pragma unroll
+        for (int k = 0; k < CAS_WPT; ++k) {
+            const int idx = tid + k * CAS_THREADS;
+            alive[k] = idx < n_act;
+            woff[k] = alive[k] ? s_woff[idx] : 0;
+            hs[k] = alive[k] ? s_score[idx] : 0.f;
+        }
+        for (int s = t; s < t_end; ++s) {
+            bool any = false;
+            if (D2) {
+                const StageD2& S = c_d2[s];
+                const float theta = S.theta;
+                const bool test = theta != -CUDART_INF_F;
+#pragma unroll
+                for (int k = 0; k < CAS_WPT; ++k) {
+                    if (alive[k]) {
+                        const float x0 = tile[woff[k] + S.off0];
+                        const bool l0 = x0 <= S.thr0;               // training.py:92 -- left iff X <= threshold
+                        const int off = l0 ? S.off1 : S.off4;
+                        const float thr = l0 ? S.thr1 : S.thr4;
+                        const float x1 = tile[woff[k] + off];
+                        const bool l1 = x1 <= thr;
+                        const float pa = l1 ? S.p2 : S.p3;
+                        const float pb = l1 ? S.p5 : S.p6;
+                        hs[k] += l0 ? pa : pb;                        // float32 accumulation in stage order
+                        ++my_weak;
+                        if (test && !(hs[k] >= theta)) alive[k] = false;   // model.py:253-258
+                        any |= alive[k];
+                    }
+                }
+            } else {
+                const NodeDev* __restrict__ nb = p.nodes + (size_t)s * p.N;
+                const float theta = __ldg(p.theta + s);
+                const bool test = theta != -CUDART_INF_F;
+#pragma unroll
+                for (int k = 0; k < CAS_WPT; ++k) {
+                    if (alive[k]) {
+                        NodeDev nd = load_node(nb);
+                        while (nd.left >= 0) {
+                            const float x = tile[woff[k] + nd.off];
+                            const int nxt = (x <= nd.thr) ? nd.left : nd.right;
+                            nd = load_node(nb + nxt);
+                        }
+                        hs[k] += nd.pred;
+                        ++my_weak;
+                        if (test && !(hs[k] >= theta)) alive[k] = false;
+                        any |= alive[k];
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, any)) break;
+        }
+        // ---- order-preserving re-pack of the CTA's survivors
+        unsigned bal[CAS_WPT];
+#pragma unroll
+        for (int k = 0; k < CAS_WPT; ++k) bal[k] = __ballot_sync(0xffffffffu, alive[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < CAS_WPT; ++k) s_tot[k * (CAS_THREADS / 32) + warp] = __popc(bal[k]);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int val = s_tot[lane];
+            int inc = val;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            s_tot[lane] = inc - val;
+            if (lane == 31) s_nact = inc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CAS_WPT; ++k) {
+            if (alive[k]) {
+                const int pos = s_tot[k * (CAS_THREADS / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+                s_woff[pos] = (unsigned short)woff[k];
+                s_score[pos] = hs[k];
+            }
+        }
+        n_act = s_nact;
+        __syncthreads();
+        t = t_end;
+    }
+
+    // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
+    for (int i = tid; i < n_act; i += CAS_THREADS) {
+        const int wo = s_woff[i];
+        const int lr = wo / pitch, lc = wo - lr * pitch;
+        const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
+        p.score[(long long)frame * p.score_stride + widx] = s_score[i];
+        atomicOr(p.mask + (long long)frame * p.mask_stride + (widx >> 5), 1u << (unsigned)(widx & 31));
+    }
+    // ---- stats (model.py:248,252): n_loc += windows, n_weak += windows entering each stage
+    unsigned w = my_weak;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+    if (lane == 0 && w) atomicAdd(p.stats + 2 * frame + 1, (unsigned long long)w);
+    if (tid == 0) atomicAdd(p.stats + 2 * frame, (unsigned long long)nwin);
+}
+
+// ------------------------------------------------------------------------------------------------ ranking
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WORDS = SCAN_THREADS * 4;
+
+__global__ void __launch_bounds__(SCAN_THREADS) mask_block_sums(const unsigned* __restrict__ mask, unsigned* __restrict__ block_sums) {
+    __shared__ unsigned s[SCAN_THREADS / 32];
+    const uint4 w = reinterpret_cast<const uint4*>(mask)[(size_t)blockIdx.x * SCAN_THREADS + threadIdx.x];
+    unsigned c = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int i = 0; i < SCAN_THREADS / 32; ++i) tot += s[i];
+        block_sums[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_block_sums(const unsigned* __restrict__ block_sums, long long* __restrict__ block_prefix,
+                                                        int n_blocks, long long* __restrict__ n_hits) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + tid;
+        const long long val = i < n_blocks ? (long long)block_sums[i] : 0;
+        long long inc = val;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const long long wv = s_warp[lane];
+            long long winc = wv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long o = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += o;
+            }
+            s_warp[lane] = winc - wv;
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long excl = carry + s_warp[warp] + inc - val;
+        if (i < n_blocks) block_prefix[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (tid == 0) *n_hits = s_carry;
+}
+
+struct EmitParams {
+    const unsigned* mask;
+    const long long* block_prefix;
+    const LevelDev* levels;
+    int n_levels;
+    long long mask_stride, total_words;
+    const float* score;
+    long long score_stride;
+    wbg_hit* hits;
+    long long hit_cap;
+    int* level_counts;
+    int m, n;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) emit_hits(const EmitParams p) {
+    __shared__ unsigned s_warp[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long w0 = ((long long)blockIdx.x * SCAN_THREADS + tid) * 4;
+    const uint4 wv = reinterpret_cast<const uint4*>(p.mask)[(size_t)blockIdx.x * SCAN_THREADS + tid];
+    const unsigned words[4] = {wv.x, wv.y, wv.z, wv.w};
+    const unsigned cnt = __popc(wv.x) + __popc(wv.y) + __popc(wv.z) + __popc(wv.w);
+    unsigned inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int i = 0; i < warp; ++i) wbase += s_warp[i];
+    if (cnt == 0) return;
+    long long rank = p.block_prefix[blockIdx.x] + wbase + (inc - cnt);
+
+    int cur_key = -1, cur_cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        unsigned bits = words[j];
+        if (!bits) continue;
+        const long long wg = w0 + j;
+        if (wg >= p.total_words) break;
+        const int frame = (int)(wg / p.mask_stride);
+        const long long slot0 = (wg - (long long)frame * p.mask_stride) * 32;
+        int lo = 0, hi = p.n_levels - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.levels[mid].win_off <= slot0) lo = mid; else hi = mid - 1;
+        }
+        const LevelDev* __restrict__ L = p.levels + lo;
+        const int key = frame * p.n_levels + lo;
+        if (key != cur_key) {
+            if (cur_cnt) atomicAdd(p.level_counts + cur_key, cur_cnt);
+            cur_key = key; cur_cnt = 0;
+        }
+        cur_cnt += __popc(bits);
+        const int win_cols = L->win_cols;
+        const float inv = L->inv_scale;
+        const long long lbase = slot0 - L->win_off;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (rank < p.hit_cap) {
+                const int wi = (int)(lbase + b);
+                const int r = wi / win_cols, c = wi - r * win_cols;
+                wbg_hit h;
+                h.frame = frame; h.level = lo; h.r = r; h.c = c;
+                h.score = p.score[(long long)frame * p.score_stride + slot0 + b];
+                // model.py:141-147 -- [c, r, c+n, r+m] as float32 times float32(1/scale)
+                h.x1 = __fmul_rn((float)c, inv);
+                h.y1 = __fmul_rn((float)r, inv);
+                h.x2 = __fmul_rn((float)(c + p.n), inv);
+                h.y2 = __fmul_rn((float)(r + p.m), inv);
+                p.hits[rank] = h;
+            }
+            ++rank;
+        }
+    }
+    if (cur_cnt) atomicAdd(p.level_counts + cur_key, cur_cnt);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct CascadeWs {
+    unsigned* mask;
+    long long mask_words_padded;
+    int n_blocks;
+    unsigned* block_sums;
+    long long* block_prefix;
+    float* score;
+    size_t total;
+};
+
+static CascadeWs carve(long long windows, int batch, void* base) {
+    CascadeWs w;
+    const long long words = windows / 32 * batch;
+    w.mask_words_padded = (long long)wbg_align_up((size_t)words, SCAN_WORDS);
+    w.n_blocks = (int)(w.mask_words_padded / SCAN_WORDS);
+    size_t off = 0;
+    char* b = (char*)base;
+    w.mask = (unsigned*)(b + off); off += wbg_align_up((size_t)w.mask_words_padded * 4, 256);
+    w.block_sums = (unsigned*)(b + off); off += wbg_align_up((size_t)w.n_blocks * 4 + 4, 256);
+    w.block_prefix = (long long*)(b + off); off += wbg_align_up((size_t)w.n_blocks * 8 + 8, 256);
+    w.score = (float*)(b + off); off += wbg_align_up((size_t)windows * batch * 4 + 4, 256);
+    w.total = off;
+    return w;
+}
+
+size_t wbg_cascade_ws_bytes(long long windows, int n_levels, int batch) {
+    (void)n_levels;
+    return carve(windows, batch, nullptr).total;
+}
+
+int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_levels, int tiles_per_frame,
+                       long long chn_stride, long long windows, const float* chns, int batch, wbg_hit* hits,
+                       long long hit_cap, int32_t* level_counts, unsigned long long* stats, long long* n_hits,
+                       void* ws, size_t ws_bytes, cudaStream_t stream) {
+    CascadeWs w = carve(windows, batch, ws);
+    WBG_REQUIRE(ws_bytes >= w.total, "cascade: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    WBG_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(unsigned long long) * 2 * batch, stream));
+    WBG_CUDA_TRY(cudaMemsetAsync(level_counts, 0, sizeof(int32_t) * (size_t)batch * n_levels, stream));
+    WBG_CUDA_TRY(cudaMemsetAsync(n_hits, 0, sizeof(long long), stream));
+    if (w.n_blocks == 0 || tiles_per_frame == 0) return WBG_OK;
+    WBG_CUDA_TRY(cudaMemsetAsync(w.mask, 0, (size_t)w.mask_words_padded * 4, stream));
+
+    CascadeParams p;
+    p.chns = chns; p.chn_stride = chn_stride; p.levels = d_levels; p.n_levels = n_levels; p.tiles_per_frame = tiles_per_frame;
+    p.nodes = model->d_nodes; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
+    p.C = model->C; p.m = model->m; p.n = model->n;
+    p.TR = model->geom.TR; p.TC = model->geom.TC; p.pitch = model->geom.pitch; p.plane = model->geom.plane;
+    p.mask = w.mask; p.mask_stride = windows / 32; p.score = w.score; p.score_stride = windows; p.stats = stats;
+
+    const long long grid = (long long)tiles_per_frame * batch;
+    WBG_REQUIRE(grid <= 0x7fffffffLL, "cascade: too many tiles (%lld)", grid);
+    const int smem = model->geom.smem_bytes;
+    if (model->all_d2) {
+        WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
+        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cascade_kernel<true><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
+    } else {
+        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cascade_kernel<false><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
+    }
+    WBG_CUDA_TRY(cudaGetLastError());
+
+    mask_block_sums<<<w.n_blocks, SCAN_THREADS, 0, stream>>>(w.mask, w.block_sums);
+    WBG_CUDA_TRY(cudaGetLastError());
+    scan_block_sums<<<1, 1024, 0, stream>>>(w.block_sums, w.block_prefix, w.n_blocks, n_hits);
+    WBG_CUDA_TRY(cudaGetLastError());
+    EmitParams e;
+    e.mask = w.mask; e.block_prefix = w.block_prefix; e.levels = d_levels; e.n_levels = n_levels;
+    e.mask_stride = windows / 32; e.total_words = windows / 32 * batch; e.score = w.score; e.score_stride = windows;
+    e.hits = hits; e.hit_cap = hit_cap; e.level_counts = level_counts; e.m = model->m; e.n = model->n;
+    emit_hits<<<w.n_blocks, SCAN_THREADS, 0, stream>>>(e);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trace / gather
+__global__ void trace_kernel(const float* __restrict__ X, int v, int C, const int* __restrict__ rs, const int* __restrict__ cs,
+                             long long K, int T, int N, const uint8_t* __restrict__ feature, const float* __restrict__ threshold,
+                             const int8_t* __restrict__ left, const int8_t* __restrict__ right, const float* __restrict__ prediction,
+                             uint8_t* __restrict__ leaf, float* __restrict__ score) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int r = rs[k], c = cs[k];
+    float hs = 0.f;
+    for (int s = 0; s < T; ++s) {
+        const size_t b = (size_t)s * N;
+        int nd = 0;
+        while (left[b + nd] >= 0) {
+            const uint8_t* f = feature + (b + nd) * 3;
+            const float x = X[((long long)(r + f[0]) * v + (c + f[1])) * C + f[2]];
+            nd = (x <= threshold[b + nd]) ? left[b + nd] : right[b + nd];
+        }
+        leaf[k * T + s] = (uint8_t)nd;
+        hs += prediction[b + nd];
+    }
+    score[k] = hs;
+}
+
+extern "C" int wbg_cascade_trace(const wbg_model* model, const float* X, int32_t u, int32_t v, const int32_t* rs,
+                                 const int32_t* cs, int64_t K, uint8_t* leaf, float* score, void* stream) {
+    WBG_REQUIRE(model && X && score && (leaf || model->T == 0), "wbg_cascade_trace: null argument");
+    WBG_REQUIRE(K >= 0 && u >= model->m && v >= model->n, "wbg_cascade_trace: bad sizes");
+    if (K == 0) return WBG_OK;
+    WBG_REQUIRE(rs && cs, "wbg_cascade_trace: null window list");
+    const int threads = 128;
+    const long long blocks = (K + threads - 1) / threads;
+    trace_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(X, v, model->C, rs, cs, K, model->T, model->N, model->d_feature,
+                                                                          model->d_threshold, model->d_left, model->d_right,
+                                                                          model->d_prediction, leaf, score);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+__global__ void gather_kernel(const float* __restrict__ X, int v, int C, const int* __restrict__ rs, const int* __restrict__ cs,
+                              long long total, int m, int n, float* __restrict__ out) {
+    const int row = n * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / ((long long)m * row);
+        const int rem = (int)(i - k * (long long)m * row);
+        const int dr = rem / row, e = rem - dr * row;
+        out[i] = __ldg(X + ((long long)(rs[k] + dr) * v + cs[k]) * C + e);
+    }
+}
+
+extern "C" int wbg_gather_samples(const float* X, int32_t u, int32_t v, int32_t c, const int32_t* rs, const int32_t* cs,
+                                  int64_t K, int32_t m, int32_t n, float* out, void* stream) {
+    WBG_REQUIRE(X && (out || K == 0), "wbg_gather_samples: null argument");
+    WBG_REQUIRE(K >= 0 && m >= 1 && n >= 1 && c >= 1 && u >= m && v >= n, "wbg_gather_samples: bad sizes");
+    if (K == 0) return WBG_OK;
+    WBG_REQUIRE(rs && cs, "wbg_gather_samples: null window list");
+    const long long total = (long long)K * m * n * c;
+    const int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gather_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(X, v, c, rs, cs, total, m, n, out);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}

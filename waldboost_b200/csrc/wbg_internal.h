@@ -1,0 +1,123 @@
+// Internal structures shared by the libwbg translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "wbg.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+void wbg_set_error(const char* fmt, ...);
+#define WBG_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            wbg_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return WBG_ECUDA;                                                                       \
+        }                                                                                           \
+    } while (0)
+#define WBG_REQUIRE(cond, ...)      \
+    do {                            \
+        if (!(cond)) {              \
+            wbg_set_error(__VA_ARGS__); \
+            return WBG_EINVAL;      \
+        }                           \
+    } while (0)
+
+static inline size_t wbg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------ geometry
+// Tile of the fused per-level channel kernel (output = pooled + smoothed channel pixels).
+constexpr int PYR_TU = 16;
+constexpr int PYR_TV = 32;
+constexpr int PYR_THREADS = 256;
+
+// Tile of the cascade kernel: TR x TC windows, channel patch (TR+m-1) x (TC+n-1) x C staged planar in smem.
+struct CascadeGeom {
+    int TR, TC;        // windows per tile
+    int rows, pitch;   // patch rows, padded row pitch (floats)
+    int plane;         // floats per channel plane
+    int smem_bytes;    // dynamic shared memory of the cascade kernel
+};
+constexpr int CAS_THREADS = 256;
+constexpr int CAS_WPT = 4;                       // window slots per thread
+constexpr int CAS_MAX_WIN = CAS_THREADS * CAS_WPT;  // windows per tile upper bound
+bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g);
+
+// Device-side description of one pyramid level (superset of wbg_level).
+struct LevelDev {
+    int oct, src_h, src_w, nh, nw, u, v, identity;
+    long long src_off;   // element offset of the octave inside one frame's octave workspace (octave >= 1)
+    long long chn_off;   // float offset inside one frame's channel block
+    long long win_off;   // first window slot of this level inside one frame (multiple of 32)
+    int win_rows, win_cols;
+    int ptile0, ptiles_x, ptiles_y;   // tiles of the channel kernel (prefix, grid)
+    int ctile0, ctiles_x, ctiles_y;   // tiles of the cascade kernel
+    float inv_scale;                  // float32(1 / scale), model.py:147
+    int pad_;
+    double zoom_r, zoom_c;            // src_h / nh, src_w / nw as float64 (scipy zoom, grid_mode=True)
+};
+
+struct OctaveInfo {
+    int h, w;
+    long long off;  // element offset in the per-frame octave workspace; octave 0 lives in the input image
+};
+
+struct wbg_plan {
+    int H = 0, W = 0, C = 0, win_m = 0, win_n = 0;
+    wbg_channel_opts opts{};
+    std::vector<OctaveInfo> octaves;
+    std::vector<wbg_level> levels;
+    std::vector<LevelDev> dev_levels;
+    long long chn_floats = 0, octave_elems = 0, windows = 0, n_loc = 0;
+    int ptiles = 0, ctiles = 0;  // tiles per frame
+    CascadeGeom geom{};
+    bool geom_ok = false;
+    int device = -1;
+    LevelDev* d_levels = nullptr;  // device copy of dev_levels
+};
+
+// Node record of the generic cascade kernel (16 bytes, read with one 128-bit load).
+struct __align__(16) NodeDev {
+    int off;          // smem offset of the feature inside the planar tile: ch*plane + r*pitch + c
+    float thr;
+    short left, right;
+    float pred;
+};
+
+// One canonical depth-2 stage for the constant-memory fast path (48 bytes).
+struct __align__(16) StageD2 {
+    int off0; float thr0;          // root
+    int off1; float thr1;          // left child
+    int off4; float thr4;          // right child
+    float p2, p3, p5, p6;          // leaves LL, LR, RL, RR
+    float theta; float pad_;
+};
+constexpr int D2_MAX_STAGES = 1280;  // 61,440 bytes of __constant__
+
+struct wbg_model {
+    int m = 0, n = 0, C = 0, T = 0, N = 0;
+    CascadeGeom geom{};
+    int device = -1;
+    bool all_d2 = false;
+    // raw arrays as uploaded (used by trace / sample paths)
+    uint8_t* d_feature = nullptr;
+    float* d_threshold = nullptr;
+    int8_t* d_left = nullptr;
+    int8_t* d_right = nullptr;
+    float* d_prediction = nullptr;
+    float* d_theta = nullptr;
+    NodeDev* d_nodes = nullptr;   // [T][N]
+    StageD2* d_d2 = nullptr;      // [T] when all_d2
+};
+
+// ------------------------------------------------------------------------------------------------ launchers
+int wbg_launch_pyramid(const wbg_plan* plan, const void* img, int dtype, int batch, float* chns, void* ws,
+                       size_t ws_bytes, cudaStream_t stream);
+int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_levels, int tiles_per_frame,
+                       long long chn_stride, long long windows, const float* chns, int batch, wbg_hit* hits,
+                       long long hit_cap, int32_t* level_counts, unsigned long long* stats, long long* n_hits,
+                       void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t wbg_cascade_ws_bytes(long long windows, int n_levels, int batch);

@@ -1,0 +1,477 @@
+// Channel pyramid for sm_100a: replaces channel_pyramid (reference waldboost/channels.py:111-146) for a batch of frames.
+//
+// Compiled with -fmad=false: the resampling and projection arithmetic below restates float64 expressions of
+// scipy / numpy whose intermediate roundings must not be contracted into FMAs (a one-ulp change before the
+// uint8 truncation of channels.py:132 changes a pixel by 1).
+//
+// Launch family per batch:
+//   minmax_kernel     per-frame min/max of the input (skimage.resize clips to the input range)
+//   octave_kernel     octave chain, 2x2 average of the *image* (channels.py:93-101, :55-64) + its min/max
+//   level_kernel      ONE launch for all levels of all frames; each CTA produces a 16x32 tile of final channel
+//                     pixels and fuses resize -> gradients -> grad_hist / grad_mag -> 2x2 shrink -> 3x3 smooth
+//                     (channels.py:132-142) through shared memory, reading the octave image and writing the
+//                     channel map exactly once.
+#include <math_constants.h>
+
+#include "wbg_internal.h"
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy 'reflect' (d c b a | a b c d | d c b a), any offset
+    if (n == 1) return 0;
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i >= n ? p - 1 - i : i;
+}
+
+__device__ __forceinline__ int f32_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_f32(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+template <typename T> __device__ __forceinline__ int mm_encode(T v);
+template <> __device__ __forceinline__ int mm_encode<uint8_t>(uint8_t v) { return (int)v; }
+template <> __device__ __forceinline__ int mm_encode<float>(float v) { return f32_to_ordered(v); }
+
+__device__ __forceinline__ void block_minmax_commit(int mn, int mx, int2* dst) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&dst->x, mn);
+        atomicMax(&dst->y, mx);
+    }
+}
+
+__global__ void minmax_init_kernel(int2* mm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mm[i] = make_int2(0x7fffffff, (int)0x80000000);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ img, long long elems, int2* mm, int n_oct) {
+    const T* p = img + (long long)blockIdx.y * elems;
+    int mn = 0x7fffffff, mx = (int)0x80000000;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x) {
+        const int e = mm_encode<T>(p[i]);
+        mn = min(mn, e);
+        mx = max(mx, e);
+    }
+    block_minmax_commit(mn, mx, mm + (long long)blockIdx.y * n_oct);
+}
+
+// channels.py:55-64 on the image: uint8 -> widened sum, true division, truncation; float32 -> ((a00+a10)+a01)+a11, /4
+__device__ __forceinline__ uint8_t pool4(uint8_t a00, uint8_t a10, uint8_t a01, uint8_t a11) {
+    return (uint8_t)(((int)a00 + (int)a10 + (int)a01 + (int)a11) >> 2);
+}
+__device__ __forceinline__ float pool4(float a00, float a10, float a01, float a11) {
+    return __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a00, a10), a01), a11), 4.0f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) octave_kernel(const T* __restrict__ src, long long src_stride, int sw, T* __restrict__ dst,
+                                                     long long dst_stride, int dh, int dw, int2* mm, int n_oct, int oct) {
+    const T* s = src + (long long)blockIdx.y * src_stride;
+    T* d = dst + (long long)blockIdx.y * dst_stride;
+    const int total = dh * dw;
+    int mn = 0x7fffffff, mx = (int)0x80000000;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / dw, x = i - y * dw;
+        const T* q = s + (long long)(2 * y) * sw + 2 * x;
+        const T o = pool4(q[0], q[sw], q[1], q[sw + 1]);
+        d[i] = o;
+        const int e = mm_encode<T>(o);
+        mn = min(mn, e);
+        mx = max(mx, e);
+    }
+    block_minmax_commit(mn, mx, mm + (long long)blockIdx.y * n_oct + oct);
+}
+
+// ------------------------------------------------------------------------------------------------ level kernel
+struct PyrParams {
+    const void* img;
+    long long img_stride;  // elements per frame
+    const void* oct_ws;
+    long long oct_stride;  // elements per frame
+    const int2* minmax;
+    int n_oct;
+    const LevelDev* levels;
+    int n_levels, tiles_per_frame;
+    float* chns;
+    long long chn_stride;
+    int C, S, smooth, kind, n_bins, full, G;
+    float bias, eps;
+    float tri[2 * WBG_MAX_NORM + 1];
+    double cs[WBG_MAX_BINS], sn[WBG_MAX_BINS];
+};
+
+struct Tap {
+    int i0, i1;
+    double w0, w1;
+};
+
+// scipy NI_ZoomShift, order 1, grid_mode: cc = (j + 0.5) * zoom - 0.5 in three float64 steps
+__device__ __forceinline__ Tap make_tap(int j, double zoom, int n_in) {
+    double cc = (double)j;
+    cc = __dadd_rn(cc, 0.5);
+    cc = __dmul_rn(cc, zoom);
+    cc = __dadd_rn(cc, -0.5);
+    const double fl = floor(cc);
+    const double t = __dadd_rn(cc, -fl);
+    int i0 = (int)fl, i1 = i0 + 1;
+    i0 = max(0, min(i0, n_in - 1));
+    if (i1 > n_in - 1) i1 = max(2 * (n_in - 1) - i1, 0);  // 'mirror'; only reached with weight 0 when down-scaling
+    Tap tp;
+    tp.i0 = i0; tp.i1 = i1;
+    tp.w0 = __dadd_rn(1.0, -t);
+    tp.w1 = t;
+    return tp;
+}
+
+template <typename T> __device__ __forceinline__ float finish_resample(double t, int mn, int mx);
+// uint8: np.clip in float64, then astype(uint8) truncates (channels.py:132)
+template <> __device__ __forceinline__ float finish_resample<uint8_t>(double t, int mn, int mx) {
+    t = fmin(fmax(t, (double)mn), (double)mx);
+    return (float)(int)t;
+}
+// float32: zoom stores float32, clip against the float32 min/max
+template <> __device__ __forceinline__ float finish_resample<float>(double t, int mn, int mx) {
+    const float f = (float)t;
+    return fminf(fmaxf(f, ordered_to_f32(mn)), ordered_to_f32(mx));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PYR_THREADS) level_kernel(const PyrParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    int lo = 0, hi = p.n_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.levels[mid].ptile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const LevelDev* __restrict__ L = p.levels + lo;
+    const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
+    const int local = tile_id - L->ptile0;
+    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ou0 = ty * PYR_TU, ov0 = tx * PYR_TV;
+
+    const int S = p.S, C = p.C, G = p.G;
+    const int hsm = p.smooth == 1 ? 1 : 0;
+    const bool has_mag = p.kind != WBG_CH_GRAD_HIST, has_hist = p.kind != WBG_CH_GRAD_MAG;
+    // region sizes (tile-relative grids, see file header)
+    const int PH = PYR_TU + 2 * hsm, PW = PYR_TV + 2 * hsm;
+    const int FH = S * PH, FW = S * PW;
+    const int MH = FH + 2 * G, MW = FW + 2 * G;
+    const int RH = MH + 2, RW = MW + 2;
+    const int fy0 = S * (ou0 - hsm), fx0 = S * (ov0 - hsm);
+    const int ry0 = fy0 - G - 1, rx0 = fx0 - G - 1;
+
+    // shared memory carve-up
+    Tap* s_tapr = reinterpret_cast<Tap*>(smem_raw);
+    Tap* s_tapc = s_tapr + RH;
+    float* s_R = reinterpret_cast<float*>(s_tapc + RW);
+    float* s_P = s_R + RH * RW;                 // [C][PH*PW]
+    float* s_M = s_P + C * PH * PW;             // [MH][MW]      (mag kinds)
+    float* s_T1 = s_M + (has_mag ? MH * MW : 0);  // [FH][MW]
+    float* s_F = s_T1 + (has_mag ? FH * MW : 0);  // [FH][FW]
+
+    const T* __restrict__ src = (L->oct == 0)
+        ? reinterpret_cast<const T*>(p.img) + (long long)frame * p.img_stride
+        : reinterpret_cast<const T*>(p.oct_ws) + (long long)frame * p.oct_stride + L->src_off;
+    const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
+    const bool identity = L->identity != 0;
+
+    // ---- phase 0: interpolation taps of the rows / columns of the (reflect-extended) resized tile
+    if (!identity) {
+        const double zr = L->zoom_r, zc = L->zoom_c;
+        for (int i = tid; i < RH + RW; i += PYR_THREADS) {
+            if (i < RH) s_tapr[i] = make_tap(reflect_idx(ry0 + i, nh), zr, sh);
+            else s_tapc[i - RH] = make_tap(reflect_idx(rx0 + (i - RH), nw), zc, sw);
+        }
+        __syncthreads();
+    }
+    // ---- phase 1: resized image tile, cast back to the input dtype (channels.py:132), as float32
+    for (int i = tid; i < RH * RW; i += PYR_THREADS) {
+        const int iy = i / RW, ix = i - iy * RW;
+        float val;
+        if (identity) {
+            val = (float)src[(long long)reflect_idx(ry0 + iy, nh) * sw + reflect_idx(rx0 + ix, nw)];
+        } else {
+            const Tap a = s_tapr[iy], b = s_tapc[ix];
+            const T* r0p = src + (long long)a.i0 * sw;
+            const T* r1p = src + (long long)a.i1 * sw;
+            const double v00 = (double)r0p[b.i0], v01 = (double)r0p[b.i1];
+            const double v10 = (double)r1p[b.i0], v11 = (double)r1p[b.i1];
+            double t = __dmul_rn(__dmul_rn(v00, a.w0), b.w0);
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(v01, a.w0), b.w1));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(v10, a.w1), b.w0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(v11, a.w1), b.w1));
+            val = finish_resample<T>(t, mm.x, mm.y);
+        }
+        s_R[i] = val;
+    }
+    __syncthreads();
+
+    // gradients at R-grid position (iy, ix), 1 <= iy < RH-1 (channels.py:16-21): each 1-D pass accumulates in
+    // float64 and stores float32; g = prev - next because convolve1d flips [-1, 0, 1]
+    auto Hc = [&](int iy, int ix) -> float {   // [1,2,1] along rows (axis 0)
+        return (float)(2.0 * (double)s_R[iy * RW + ix] + ((double)s_R[(iy - 1) * RW + ix] + (double)s_R[(iy + 1) * RW + ix]));
+    };
+    auto Hr = [&](int iy, int ix) -> float {   // [1,2,1] along columns (axis 1)
+        return (float)(2.0 * (double)s_R[iy * RW + ix] + ((double)s_R[iy * RW + ix - 1] + (double)s_R[iy * RW + ix + 1]));
+    };
+    auto grad = [&](int iy, int ix, float& gx, float& gy) {
+        gx = __fsub_rn(Hc(iy, ix - 1), Hc(iy, ix + 1));
+        gy = __fsub_rn(Hr(iy - 1, ix), Hr(iy + 1, ix));
+    };
+
+    if (has_mag) {
+        // ---- phase 2: gradient magnitude on the extended grid (channels.py:31-32), float32 throughout
+        for (int i = tid; i < MH * MW; i += PYR_THREADS) {
+            const int iy = i / MW, ix = i - iy * MW;
+            float gx, gy;
+            grad(iy + 1, ix + 1, gx, gy);
+            s_M[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+        }
+        __syncthreads();
+        if (G > 0) {
+            // ---- phase 3: triangle normalisation (channels.py:33-36): axis 0 then axis 1, float64 accumulate in
+            // scipy's symmetric order, float32 between passes
+            for (int i = tid; i < FH * MW; i += PYR_THREADS) {
+                const int iy = i / MW, ix = i - iy * MW;
+                const float* c = s_M + (iy + G) * MW + ix;
+                double acc = (double)c[0] * (double)p.tri[G];
+                for (int k = -G; k < 0; ++k) acc += ((double)c[k * MW] + (double)c[-k * MW]) * (double)p.tri[G + k];
+                s_T1[i] = (float)acc;
+            }
+            __syncthreads();
+            for (int i = tid; i < FH * FW; i += PYR_THREADS) {
+                const int iy = i / FW, ix = i - iy * FW;
+                const float* c = s_T1 + iy * MW + ix + G;
+                double acc = (double)c[0] * (double)p.tri[G];
+                for (int k = -G; k < 0; ++k) acc += ((double)c[k] + (double)c[-k]) * (double)p.tri[G + k];
+                const float nrm = (float)acc;
+                s_F[i] = __fdiv_rn(s_M[(iy + G) * MW + ix + G], __fadd_rn(nrm, p.eps));
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- phase 4: channels at full resolution + 2x2 shrink (channels.py:136-139) into the pooled tile
+    const int first_hist = has_mag ? 1 : 0;
+    for (int i = tid; i < PH * PW; i += PYR_THREADS) {
+        const int py = i / PW, px = i - py * PW;
+        const int pu = ou0 - hsm + py, pv = ov0 - hsm + px;
+        if (pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
+        float acc[WBG_MAX_CHANNELS];
+#pragma unroll 1
+        for (int sub = 0; sub < S * S; ++sub) {
+            // order of channels.py:61-64: a00, a10 (next row), a01 (next column), a11
+            const int dy = sub & 1, dx = sub >> 1;
+            const int fy = S * py + dy, fx = S * px + dx;  // full-res tile coordinates
+            if (has_mag) {
+                const float mval = G > 0 ? s_F[fy * FW + fx] : s_M[fy * MW + fx];
+                acc[0] = sub == 0 ? mval : __fadd_rn(acc[0], mval);
+            }
+            if (has_hist) {
+                float gx, gy;
+                grad(fy + G + 1, fx + G + 1, gx, gy);
+                const double gxd = (double)gx, gyd = (double)gy;
+                for (int b = 0; b < p.n_bins; ++b) {
+                    // channels.py:50 under NumPy 2: float64 products and difference, one rounding to float32
+                    const float ch = (float)__dadd_rn(__dmul_rn(gxd, p.cs[b]), -__dmul_rn(gyd, p.sn[b]));
+                    float val = fmaxf(__fsub_rn(fabsf(ch), p.bias), 0.f);
+                    if (p.full) val = __fmul_rn((float)((ch > 0.f) - (ch < 0.f)), val);
+                    acc[first_hist + b] = sub == 0 ? val : __fadd_rn(acc[first_hist + b], val);
+                }
+            }
+        }
+        for (int c = 0; c < C; ++c) s_P[c * PH * PW + i] = S == 2 ? __fdiv_rn(acc[c], 4.0f) : acc[c];
+    }
+    __syncthreads();
+
+    // ---- phase 5: 3x3 smoothing with a zero border ring (channels.py:78-90) and the HWC store
+    float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
+    for (int i = tid; i < PYR_TU * PYR_TV * C; i += PYR_THREADS) {
+        const int c = i % C, pix = i / C;
+        const int oy = pix / PYR_TV, ox = pix - oy * PYR_TV;
+        const int ou = ou0 + oy, ov = ov0 + ox;
+        if (ou >= u || ov >= v) continue;
+        float r;
+        if (hsm) {
+            if (ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1) {
+                r = 0.f;
+            } else {
+                const float* q = s_P + c * PH * PW + (oy + 1) * PW + (ox + 1);
+                double a = (double)q[-PW - 1] + 2.0 * (double)q[-PW];
+                a += (double)q[-PW + 1];
+                a += 2.0 * (double)q[-1];
+                a += 4.0 * (double)q[0];
+                a += 2.0 * (double)q[1];
+                a += (double)q[PW - 1];
+                a += 2.0 * (double)q[PW];
+                a += (double)q[PW + 1];
+                r = (float)(a / 16.0);
+            }
+        } else {
+            r = s_P[c * PH * PW + oy * PW + ox];
+        }
+        out[((long long)ou * v + ov) * C + c] = r;
+    }
+}
+
+static size_t level_smem_bytes(const wbg_channel_opts& o, int C) {
+    const int S = o.shrink, hsm = o.smooth == 1 ? 1 : 0;
+    const bool has_mag = o.kind != WBG_CH_GRAD_HIST;
+    const int G = (has_mag && o.norm > 1) ? o.norm : 0;
+    const int PH = PYR_TU + 2 * hsm, PW = PYR_TV + 2 * hsm, FH = S * PH, FW = S * PW, MH = FH + 2 * G, MW = FW + 2 * G;
+    const int RH = MH + 2, RW = MW + 2;
+    size_t b = (size_t)(RH + RW) * sizeof(Tap) + (size_t)RH * RW * 4 + (size_t)C * PH * PW * 4;
+    if (has_mag) b += (size_t)(MH * MW + FH * MW + FH * FW) * 4;
+    return b + 64;
+}
+
+template <typename T>
+static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float* chns, void* ws, cudaStream_t stream) {
+    const int n_oct = (int)plan->octaves.size();
+    const size_t esz = sizeof(T);
+    const size_t oct_bytes = wbg_align_up((size_t)plan->octave_elems * esz, 256);
+    T* oct_ws = reinterpret_cast<T*>(ws);
+    int2* mm = reinterpret_cast<int2*>((char*)ws + oct_bytes * (size_t)batch);
+    const long long oct_stride = (long long)(oct_bytes / esz);
+    const long long img_stride = (long long)plan->H * plan->W;
+
+    const int n_mm = batch * n_oct;
+    minmax_init_kernel<<<(n_mm + 255) / 256, 256, 0, stream>>>(mm, n_mm);
+    WBG_CUDA_TRY(cudaGetLastError());
+    {
+        int bx = (int)((img_stride + 256 * 16 - 1) / (256 * 16));
+        if (bx > 1024) bx = 1024;
+        if (bx < 1) bx = 1;
+        minmax_kernel<T><<<dim3(bx, batch), 256, 0, stream>>>(img, img_stride, mm, n_oct);
+        WBG_CUDA_TRY(cudaGetLastError());
+    }
+    for (int k = 1; k < n_oct; ++k) {
+        const OctaveInfo& a = plan->octaves[k - 1];
+        const OctaveInfo& b = plan->octaves[k];
+        const T* src = k == 1 ? img : oct_ws + a.off;
+        const long long src_stride = k == 1 ? img_stride : oct_stride;
+        int bx = (b.h * b.w + 255) / 256;
+        if (bx > 2048) bx = 2048;
+        octave_kernel<T><<<dim3(bx, batch), 256, 0, stream>>>(src, src_stride, a.w, oct_ws + b.off, oct_stride, b.h, b.w, mm, n_oct, k);
+        WBG_CUDA_TRY(cudaGetLastError());
+    }
+
+    const wbg_channel_opts& o = plan->opts;
+    PyrParams p;
+    memset(&p, 0, sizeof(p));
+    p.img = img; p.img_stride = img_stride; p.oct_ws = oct_ws; p.oct_stride = oct_stride; p.minmax = mm; p.n_oct = n_oct;
+    p.levels = plan->d_levels; p.n_levels = (int)plan->levels.size(); p.tiles_per_frame = plan->ptiles;
+    p.chns = chns; p.chn_stride = plan->chn_floats;
+    p.C = plan->C; p.S = o.shrink; p.smooth = o.smooth; p.kind = o.kind; p.n_bins = o.kind == WBG_CH_GRAD_MAG ? 0 : o.n_bins;
+    p.full = o.full; p.bias = o.bias; p.eps = o.eps;
+    p.G = (o.kind != WBG_CH_GRAD_HIST && o.norm > 1) ? o.norm : 0;
+    if (p.G > 0) {
+        // channels.py:11-13 -- ([1..n+1..1]).astype(f) / sum, float32 division
+        const int n = p.G;
+        const float sum = (float)((n + 1) * (n + 1));
+        for (int k = 0; k <= 2 * n; ++k) p.tri[k] = (float)(k <= n ? k + 1 : 2 * n + 1 - k) / sum;
+    }
+    for (int b = 0; b < WBG_MAX_BINS; ++b) { p.cs[b] = o.cos_t[b]; p.sn[b] = o.sin_t[b]; }
+
+    const size_t smem = level_smem_bytes(o, plan->C);
+    WBG_REQUIRE(smem <= 220 * 1024, "channel pyramid: tile needs %zu bytes of shared memory", smem);
+    WBG_CUDA_TRY(cudaFuncSetAttribute(level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (long long)plan->ptiles * batch;
+    WBG_REQUIRE(grid <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid);
+    level_kernel<T><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+int wbg_launch_pyramid(const wbg_plan* plan, const void* img, int dtype, int batch, float* chns, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+    (void)ws_bytes;
+    if (dtype == WBG_U8) return launch_pyramid_t<uint8_t>(plan, (const uint8_t*)img, batch, chns, ws, stream);
+    return launch_pyramid_t<float>(plan, (const float*)img, batch, chns, ws, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ single-map primitives
+__global__ void pool2_kernel(const float* __restrict__ in, int v, int c, float* __restrict__ out, int ou, int ov, int is_max) {
+    const long long total = (long long)ou * ov * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const long long pix = i / c;
+        const int y = (int)(pix / ov), x = (int)(pix - (long long)y * ov);
+        const float* q = in + ((long long)(2 * y) * v + 2 * x) * c + ch;
+        const float a00 = q[0], a10 = q[(long long)v * c], a01 = q[c], a11 = q[(long long)v * c + c];
+        // channels.py:61-64 / :73-75
+        out[i] = is_max ? fmaxf(fmaxf(a00, a10), fmaxf(a01, a11))
+                        : __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a00, a10), a01), a11), 4.0f);
+    }
+}
+
+__global__ void smooth_kernel(const float* __restrict__ in, int u, int v, int c, float* __restrict__ out) {
+    const long long total = (long long)u * v * c;
+    const long long rs = (long long)v * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / c;
+        const int y = (int)(pix / v), x = (int)(pix - (long long)y * v);
+        float r = 0.f;
+        if (y > 0 && x > 0 && y < u - 1 && x < v - 1) {
+            const float* q = in + i;
+            double a = (double)q[-rs - c] + 2.0 * (double)q[-rs];
+            a += (double)q[-rs + c];
+            a += 2.0 * (double)q[-c];
+            a += 4.0 * (double)q[0];
+            a += 2.0 * (double)q[c];
+            a += (double)q[rs - c];
+            a += 2.0 * (double)q[rs];
+            a += (double)q[rs + c];
+            r = (float)(a / 16.0);
+        }
+        out[i] = r;
+    }
+}
+
+static int grid_for(long long total) {
+    long long b = (total + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int wbg_avg_pool_2(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream) {
+    WBG_REQUIRE(u >= 0 && v >= 0 && c >= 1, "wbg_avg_pool_2: bad sizes");
+    const int ou = u / 2, ov = v / 2;
+    if ((long long)ou * ov == 0) return WBG_OK;
+    WBG_REQUIRE(in && out, "wbg_avg_pool_2: null argument");
+    pool2_kernel<<<grid_for((long long)ou * ov * c), 256, 0, (cudaStream_t)stream>>>(in, v, c, out, ou, ov, 0);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+extern "C" int wbg_max_pool_2(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream) {
+    WBG_REQUIRE(u >= 0 && v >= 0 && c >= 1, "wbg_max_pool_2: bad sizes");
+    const int ou = u / 2, ov = v / 2;
+    if ((long long)ou * ov == 0) return WBG_OK;
+    WBG_REQUIRE(in && out, "wbg_max_pool_2: null argument");
+    pool2_kernel<<<grid_for((long long)ou * ov * c), 256, 0, (cudaStream_t)stream>>>(in, v, c, out, ou, ov, 1);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+extern "C" int wbg_smooth_image_3d(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream) {
+    WBG_REQUIRE(u >= 0 && v >= 0 && c >= 1, "wbg_smooth_image_3d: bad sizes");
+    if ((long long)u * v == 0) return WBG_OK;
+    WBG_REQUIRE(in && out, "wbg_smooth_image_3d: null argument");
+    smooth_kernel<<<grid_for((long long)u * v * c), 256, 0, (cudaStream_t)stream>>>(in, u, v, c, out);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}

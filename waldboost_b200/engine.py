@@ -1,0 +1,362 @@
+"""Host-side driver of libwbg: plans, device buffers and launches.  PyTorch is used only as the device-memory and
+stream carrier; every computation is a C-ABI call into the CUDA library (include/wbg.h).  No CPU fallback."""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _native as N
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def get_engine(device=None):
+    """Engine bound to one CUDA device (default: the current one).  Raises without a GPU."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("waldboost_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    with _lock:
+        eng = _engines.get(idx)
+        if eng is None:
+            eng = _engines[idx] = Engine(idx)
+    return eng
+
+
+def make_channel_opts(channel_opts, spec, max_levels=0):
+    """dict + resolved channel spec -> wbg_channel_opts.  cos/sin exactly as reference channels.py:43-46."""
+    o = N.ChannelOpts()
+    o.shrink = int(channel_opts["shrink"])
+    o.n_per_oct = int(channel_opts["n_per_oct"])
+    o.smooth = int(channel_opts["smooth"])
+    o.kind = spec["kind"]
+    o.n_bins = int(spec["n_bins"])
+    o.full = 1 if spec["full"] else 0
+    o.bias = float(spec["bias"])
+    o.norm = int(spec["norm"] or 0)
+    o.eps = float(spec["eps"])
+    o.max_levels = int(max_levels)
+    if o.n_bins > N.WBG_MAX_BINS:
+        raise ValueError(f"n_bins must be <= {N.WBG_MAX_BINS}")
+    if o.n_bins > 0:
+        max_theta = 2 * np.pi if spec["full"] else np.pi
+        theta = np.linspace(0, max_theta, o.n_bins + 1)
+        cs, sn = np.cos(theta[:-1]), np.sin(theta[:-1])
+        for i in range(o.n_bins):
+            o.cos_t[i] = cs[i]
+            o.sin_t[i] = sn[i]
+    return o
+
+
+def _opts_key(channel_opts, spec, max_levels):
+    return (int(channel_opts["shrink"]), int(channel_opts["n_per_oct"]), int(channel_opts["smooth"]), spec["kind"],
+            int(spec["n_bins"]), bool(spec["full"]), float(spec["bias"]), int(spec["norm"] or 0), float(spec["eps"]),
+            int(max_levels))
+
+
+class Plan:
+    """Pyramid geometry for one (H, W, channel options, window) -- wraps a wbg_plan handle."""
+
+    def __init__(self, H, W, copts, win_m, win_n, device_tables=True):
+        L = N.lib()
+        self.handle = C.c_void_p()
+        code = L.wbg_plan_create(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, C.byref(self.handle))
+        if code == N.WBG_EINVAL and "Shrink factor" in N.last_error():
+            raise AssertionError(N.last_error())          # reference channels.py:120 is an assert
+        N.check(code)
+        self.info = N.PlanInfo()
+        N.check(L.wbg_plan_get_info(self.handle, C.byref(self.info)))
+        n = self.info.n_levels
+        arr = (N.Level * max(n, 1))()
+        N.check(L.wbg_plan_get_levels(self.handle, arr, max(n, 1)))
+        self.levels = [arr[i] for i in range(n)]
+        self.n_levels = n
+        self.C = self.info.channels
+        self.chn_floats = self.info.chn_floats
+        self.scales = [lv.scale for lv in self.levels]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                N.lib().wbg_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def plan_geometry(H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0):
+    """Host-only plan (no GPU needed): level sizes, offsets and window counts."""
+    return Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, device_tables=False)
+
+
+class ModelHandle:
+    def __init__(self, shape, trees, thetas):
+        """trees: list of objects with feature/threshold/left/right/prediction arrays (training.DTree)."""
+        m, n, ch = (int(x) for x in shape)
+        T = len(trees)
+        Nn = max([len(t.left) for t in trees] + [1])
+        n_nodes = np.zeros(max(T, 1), np.int32)
+        feature = np.zeros((max(T, 1), Nn, 3), np.uint8)
+        threshold = np.zeros((max(T, 1), Nn), np.float32)
+        left = np.full((max(T, 1), Nn), -1, np.int8)
+        right = np.full((max(T, 1), Nn), -1, np.int8)
+        prediction = np.zeros((max(T, 1), Nn), np.float32)
+        for t, tr in enumerate(trees):
+            k = len(tr.left)
+            n_nodes[t] = k
+            feature[t, :k] = np.asarray(tr.feature, np.uint8).reshape(-1, 3)
+            threshold[t, :k] = tr.threshold
+            left[t, :k] = tr.left
+            right[t, :k] = tr.right
+            prediction[t, :k] = tr.prediction
+        # NumPy compares the float32 scores with a (weak) Python-float theta in float32 (model.py:255)
+        with np.errstate(over="ignore"):
+            theta = np.asarray([float(x) for x in thetas] + ([] if T else [0.0]), np.float64).astype(np.float32)
+        d = N.ModelDesc()
+        d.win_m, d.win_n, d.channels, d.n_stages, d.max_nodes = m, n, ch, T, Nn
+        keep = (n_nodes, feature, threshold, left, right, prediction, theta)
+        d.n_nodes, d.feature, d.threshold = n_nodes.ctypes.data, feature.ctypes.data, threshold.ctypes.data
+        d.left, d.right, d.prediction, d.theta = left.ctypes.data, right.ctypes.data, prediction.ctypes.data, theta.ctypes.data
+        self.handle = C.c_void_p()
+        code = N.lib().wbg_model_create(C.byref(d), C.byref(self.handle))
+        del keep
+        if code == N.WBG_EINVAL:
+            raise ValueError(N.last_error())
+        N.check(code)
+        self.shape = (m, n, ch)
+        self.T = T
+
+    def __del__(self):
+        try:
+            if self.handle:
+                N.lib().wbg_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device_index):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device("cuda", device_index)
+        self.lib = N.lib()
+        self._plans = {}
+        self._bufs = {}
+        self._pinned = {}
+
+    # ------------------------------------------------------------------------------------------- resources
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def buffer(self, name, nbytes):
+        """Grow-only cached device byte buffer (256-byte aligned by the torch allocator)."""
+        t = self._bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = None
+            self._bufs.pop(name, None)
+            t = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def pinned(self, name, nbytes):
+        t = self._pinned.get(name)
+        if t is None or t.numel() < nbytes:
+            t = self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, pin_memory=True)
+            self._pinned[name] = t
+        return t
+
+    def plan(self, H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0):
+        key = (H, W, win_m, win_n) + _opts_key(channel_opts, spec, max_levels)
+        p = self._plans.get(key)
+        if p is None:
+            with self.torch.cuda.device(self.device):
+                p = Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n)
+            if len(self._plans) > 64:
+                self._plans.clear()
+            self._plans[key] = p
+        return p
+
+    # ------------------------------------------------------------------------------------------- pyramid
+    @staticmethod
+    def image_dtype(dtype):
+        if dtype == np.uint8:
+            return N.WBG_U8
+        if dtype == np.float32:
+            return N.WBG_F32
+        raise TypeError(f"image dtype {dtype} is not supported on the GPU path (uint8 and float32 only; no CPU fallback)")
+
+    def upload_images(self, images):
+        """numpy [B,H,W] (uint8 / float32) -> device tensor through a cached pinned staging buffer."""
+        torch = self.torch
+        images = np.ascontiguousarray(images)
+        self.image_dtype(images.dtype)
+        nbytes = images.nbytes
+        stage = self.pinned("img", nbytes)
+        stage_np = stage.numpy()[:nbytes].view(images.dtype).reshape(images.shape)
+        np.copyto(stage_np, images)
+        tdt = torch.uint8 if images.dtype == np.uint8 else torch.float32
+        dev = self.buffer("img", nbytes)[:nbytes].view(tdt).view(images.shape)
+        dev.copy_(stage[:nbytes].view(tdt).view(images.shape), non_blocking=True)
+        return dev
+
+    def pyramid(self, img_dev, plan, out=None):
+        """img_dev: device tensor [B,H,W] uint8/float32 -> chns device tensor [B, chn_floats] float32."""
+        torch = self.torch
+        B = int(img_dev.shape[0])
+        dt = N.WBG_U8 if img_dev.dtype == torch.uint8 else N.WBG_F32
+        assert img_dev.is_contiguous() and img_dev.shape[1] == plan.info.H and img_dev.shape[2] == plan.info.W
+        if out is None:
+            out = self.buffer("chns", 4 * B * max(plan.chn_floats, 1))[:4 * B * plan.chn_floats].view(torch.float32).view(B, plan.chn_floats)
+        wsb = self.lib.wbg_pyramid_workspace_bytes(plan.handle, dt, B)
+        ws = self.buffer("pyr_ws", wsb)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.wbg_channel_pyramid(plan.handle, C.c_void_p(img_dev.data_ptr()), dt, B,
+                                                 C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                 self._stream()))
+        return out
+
+    def split_levels(self, chns_row_np, plan):
+        """one frame's channel block (numpy, host) -> list of (u,v,C) views."""
+        out = []
+        for lv in plan.levels:
+            n = lv.u * lv.v * plan.C
+            out.append(chns_row_np[lv.chn_off:lv.chn_off + n].reshape(lv.u, lv.v, plan.C))
+        return out
+
+    def channel_levels(self, image, channel_opts, spec, max_levels=0):
+        """[(chns, scale)] for one image -- host copies, like the reference generator's yields."""
+        image = np.ascontiguousarray(image)
+        H, W = image.shape
+        plan = self.plan(H, W, channel_opts, spec, 0, 0, max_levels)
+        if plan.n_levels == 0:
+            return []
+        dev = self.upload_images(image[None])
+        chns = self.pyramid(dev, plan)
+        host = chns[0].cpu().numpy()
+        return [(lv.copy(), s) for lv, s in zip(self.split_levels(host, plan), plan.scales)]
+
+    # ------------------------------------------------------------------------------------------- cascade
+    def _meta(self, B, n_levels):
+        """one device buffer holding [n_hits i64][stats u64 x 2B][level_counts i32 x B*L] -> sub-pointers."""
+        nbytes = 8 + 16 * B + 4 * B * n_levels
+        t = self.buffer("meta", nbytes)
+        base = t.data_ptr()
+        return t, nbytes, base, base + 8, base + 8 + 16 * B
+
+    def _read_meta(self, t, nbytes, B, n_levels):
+        host = self.pinned("meta", nbytes)
+        host[:nbytes].copy_(t[:nbytes], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        raw = host.numpy()[:nbytes]
+        n_hits = int(raw[:8].view(np.int64)[0])
+        stats = raw[8:8 + 16 * B].view(np.uint64).reshape(B, 2).copy()
+        counts = raw[8 + 16 * B:nbytes].view(np.int32).reshape(B, n_levels).copy()
+        return n_hits, stats, counts
+
+    def _read_hits(self, hits_t, n):
+        if n == 0:
+            return np.empty(0, N.HIT_DTYPE)
+        nb = n * N.HIT_DTYPE.itemsize
+        host = self.pinned("hits", nb)
+        host[:nb].copy_(hits_t[:nb], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()[:nb].view(N.HIT_DTYPE).copy()
+
+    def cascade(self, model_handle, plan, chns, B, hit_cap=None):
+        """Run the cascade over every level of B frames.  Returns (hits, level_counts [B,L], stats [B,2])."""
+        lib = self.lib
+        if hit_cap is None:
+            hit_cap = int(min(max(plan.info.n_loc * B, 1), 1 << 20))
+        wsb = lib.wbg_cascade_workspace_bytes(plan.handle, B)
+        ws = self.buffer("cas_ws", wsb)
+        while True:
+            hits_t = self.buffer("hits", hit_cap * N.HIT_DTYPE.itemsize)
+            meta, nbytes, p_nhits, p_stats, p_counts = self._meta(B, plan.n_levels)
+            with self.torch.cuda.device(self.device):
+                code = lib.wbg_cascade_scan(model_handle.handle, plan.handle, C.c_void_p(chns.data_ptr()), B,
+                                            C.c_void_p(hits_t.data_ptr()), hit_cap, C.c_void_p(p_counts),
+                                            C.c_void_p(p_stats), C.c_void_p(p_nhits), C.c_void_p(ws.data_ptr()),
+                                            ws.numel(), self._stream())
+            if code == N.WBG_EINVAL and "Invalid number of channels" in N.last_error():
+                raise AssertionError(N.last_error())       # reference model.py:238 is an assert
+            N.check(code)
+            n_hits, stats, counts = self._read_meta(meta, nbytes, B, plan.n_levels)
+            if n_hits <= hit_cap:
+                return self._read_hits(hits_t, n_hits), counts, stats
+            hit_cap = n_hits  # WBG_ECAP semantics: only the first hit_cap were stored -> re-run with room for all
+
+    def predict_on_map(self, model_handle, X, hit_cap=None):
+        """Model.predict_on_image on one channel map X (numpy or device tensor, (u,v,C) float32)."""
+        torch, lib = self.torch, self.lib
+        m, n, ch = model_handle.shape
+        if isinstance(X, np.ndarray):
+            X = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
+        u, v = int(X.shape[0]), int(X.shape[1])
+        n_loc = max(u - m, 0) * max(v - n, 0)
+        if hit_cap is None:
+            hit_cap = int(min(max(n_loc, 1), 1 << 20))
+        wsb = lib.wbg_predict_workspace_bytes(u, v, m, n)
+        ws = self.buffer("cas_ws", wsb)
+        if X.numel() == 0:
+            X = torch.zeros(4, dtype=torch.float32, device=self.device)
+        while True:
+            hits_t = self.buffer("hits", hit_cap * N.HIT_DTYPE.itemsize)
+            meta, nbytes, p_nhits, p_stats, _ = self._meta(1, 1)
+            with torch.cuda.device(self.device):
+                N.check(lib.wbg_predict_on_image(model_handle.handle, C.c_void_p(X.data_ptr()), u, v,
+                                                 C.c_void_p(hits_t.data_ptr()), hit_cap, C.c_void_p(p_stats),
+                                                 C.c_void_p(p_nhits), C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
+            n_hits, stats, _ = self._read_meta(meta, nbytes, 1, 1)
+            if n_hits <= hit_cap:
+                return self._read_hits(hits_t, n_hits), stats[0]
+            hit_cap = n_hits
+
+    def trace(self, model_handle, X, rs, cs):
+        """(leaf [K,T] uint8, score [K] float32) for explicit windows, no rejection (wbg_cascade_trace)."""
+        torch = self.torch
+        Xd = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
+        rs_d = torch.from_numpy(np.ascontiguousarray(rs, np.int32)).to(self.device)
+        cs_d = torch.from_numpy(np.ascontiguousarray(cs, np.int32)).to(self.device)
+        K, T = int(rs_d.numel()), model_handle.T
+        leaf = torch.zeros((K, max(T, 1)), dtype=torch.uint8, device=self.device)
+        score = torch.zeros(K, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.wbg_cascade_trace(model_handle.handle, C.c_void_p(Xd.data_ptr()), int(Xd.shape[0]), int(Xd.shape[1]),
+                                               C.c_void_p(rs_d.data_ptr()), C.c_void_p(cs_d.data_ptr()), K,
+                                               C.c_void_p(leaf.data_ptr()), C.c_void_p(score.data_ptr()), self._stream()))
+        return leaf.cpu().numpy()[:, :T], score.cpu().numpy()
+
+    def gather_samples(self, X, rs, cs, shape):
+        torch = self.torch
+        m, n = int(shape[0]), int(shape[1])
+        Xd = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
+        ch = int(Xd.shape[2])
+        rs_d = torch.from_numpy(np.ascontiguousarray(rs, np.int32)).to(self.device)
+        cs_d = torch.from_numpy(np.ascontiguousarray(cs, np.int32)).to(self.device)
+        K = int(rs_d.numel())
+        out = torch.empty((K, m, n, ch), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.wbg_gather_samples(C.c_void_p(Xd.data_ptr()), int(Xd.shape[0]), int(Xd.shape[1]), ch,
+                                                C.c_void_p(rs_d.data_ptr()), C.c_void_p(cs_d.data_ptr()), K, m, n,
+                                                C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+    def map_primitive(self, fn_name, arr, out_shape):
+        torch = self.torch
+        a3 = arr.reshape(arr.shape[0], arr.shape[1], -1)
+        Xd = torch.from_numpy(np.ascontiguousarray(a3, np.float32)).to(self.device)
+        out = torch.zeros(int(np.prod(out_shape)) if len(out_shape) else 1, dtype=torch.float32, device=self.device)
+        if Xd.numel() and out.numel():
+            with torch.cuda.device(self.device):
+                N.check(getattr(self.lib, fn_name)(C.c_void_p(Xd.data_ptr()), a3.shape[0], a3.shape[1], a3.shape[2],
+                                                   C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()[:int(np.prod(out_shape))].reshape(out_shape)
