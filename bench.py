@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p frames/s of Model.detect (BASELINE.json metric) on B200, with the HBM roofline of the two dominant
+kernels and the CPU reference path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--profile wald|dense] [--impl reference]
+
+Workload (BASELINE.json configs[1] / configs[4]): a batch of 64 synthetic 1920x1080 uint8 frames per GPU and the
+12x12x4 grad_hist model (shrink 2, n_per_oct 8, smooth 1) with 1024 depth-2 stages and 'wald' rejection thresholds
+(tests/golden/configB_model.pb, calibrated with the reference).  One "step" = detect() over one batch on
+every rank.  N > 1: one process per GPU (torchrun), frames sharded by image, no data-path collective; the process group
+is used only for the barrier and the max-over-ranks of the step time ("scaling": "weak").
+
+  value     frames/s with the frames already resident in HBM: fused channel pyramid + cascade + hit emission.
+  e2e       frames/s through the public API (Model.detect_batch on pinned HOST frames): H2D copy of the frames and D2H
+            read of the hits inside the timed region.
+  roofline  for the kernel with the larger share of the step: ALGORITHMIC bytes per launch / its CUDA-event time;
+            `roofline_pyramid` and `roofline_cascade` give both kernels.
+  cpu_baseline  the oracle (a NumPy restatement of the reference's own algorithm, oracle/wb_oracle.py) on the host
+            cores, image-sharded over worker processes, on a bounded sample of the same workload.
+
+--impl reference times only that CPU path and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_B = os.path.join(ROOT, "tests", "golden", "configB_model.pb")
+H, W = 1080, 1920
+METRIC = "1080p frames/sec for Model.detect"
+UNIT = "frames/s"
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference path
+def _cpu_worker(job):
+    """One worker process: oracle detect() on `n` 1080p frames (seed0 ..).  Imports the oracle only here."""
+    seed0, n, profile, h, w = job
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import wb_oracle as O  # noqa: F401  (checker / CPU baseline only)
+    import waldboost_b200 as wb
+    from helpers import oracle_cascade
+    from waldboost_b200 import synthetic as S
+    M = wb.Model.load(MODEL_B)
+    if profile == "dense":
+        M.theta = [-np.inf] * len(M)
+    Cs = oracle_cascade(M)
+    frames = [S.synthetic_frame(seed0 + i, h, w) for i in range(n)]
+    t0 = time.perf_counter()
+    hits = 0
+    for f in frames:
+        hits += Cs.detect(f)[1].size
+    return time.perf_counter() - t0, hits, Cs.n_loc, Cs.n_weak
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuPool:
+    """Image-sharded worker processes (the reference's own parallel pattern: multiprocessing.Pool over files,
+    scripts/waldboost-detect.py:65), spawned so they never inherit a CUDA context."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context("spawn").Pool(workers)
+
+    def step(self, frames_per_worker, profile, h=H, w=W, seed0=1000):
+        jobs = [(seed0 + k * frames_per_worker, frames_per_worker, profile, h, w) for k in range(self.workers)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        busy = max(r[0] for r in res)            # exclude process start-up / frame synthesis: slowest worker's detect time
+        return wall, busy, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on all host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = max(1, min(host_cores(), args.cpu_workers or 10 ** 6))
+    pool = CpuPool(cores)
+    for _ in range(args.warmup):                 # untimed: a small frame per worker (imports, page-in; there is no JIT)
+        pool.step(1, args.profile, 135, 240)
+    t = 0.0
+    frames = 0
+    for _ in range(args.steps):
+        _, busy, _, _, _ = pool.step(1, args.profile)
+        t += busy
+        frames += cores
+    pool.close()
+    fps = frames / t
+    sample = f"{cores} frames of 1920x1080 per step (one per worker process), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Model.detect, 1920x1080 uint8 frames, 12x12x4 grad_hist model, 1024 depth-2 stages, {args.profile} thetas",
+                   "profile": args.profile},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(plan, dtype_bytes, n_hits_per_frame=0.0):
+    """SURVEY.md 8d per frame: pyramid = read the source once + write every level once;
+    cascade = read every level once + write the hits."""
+    chn = 4 * plan.C * sum(lv.u * lv.v for lv in plan.levels)
+    pyr = plan.info.H * plan.info.W * dtype_bytes + chn
+    cas = chn + 36 * n_hits_per_frame
+    return pyr, cas
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- CPU baseline first (rank 0 at N=1 only), before this process's CUDA work starts: bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = max(1, min(host_cores(), args.cpu_workers or 32))
+        pool = CpuPool(cores)
+        pool.step(1, args.profile, 135, 240)
+        _, busy, _, n_loc_c, n_weak_c = pool.step(1, args.profile)
+        pool.close()
+        cpu = {"value": cores / busy, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} frames of 1920x1080 (one per worker process), oracle/wb_oracle.py Cascade.detect, "
+                         f"eval_cost {n_weak_c / max(n_loc_c, 1):.1f}, {busy:.1f} s"}
+
+    from __graft_entry__ import build
+    if local == 0:
+        build()
+    barrier()
+    import waldboost_b200 as wb
+    from waldboost_b200 import synthetic as S
+    from waldboost_b200.engine import get_engine
+
+    B = args.batch
+    model = wb.Model.load(MODEL_B)
+    if args.profile == "dense":
+        model.theta = [-np.inf] * len(model)
+    eng = get_engine()
+
+    # ---- synthetic frames, page-locked on the host (frame i of rank r uses seed 1000 + r*B + i)
+    uniq = min(B, args.unique_frames)
+    pinned = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+    frames = pinned.numpy()
+    for i in range(uniq):
+        frames[i] = S.synthetic_frame(1000 + rank * B + i, H, W)
+    for i in range(uniq, B):
+        frames[i] = frames[i % uniq]
+
+    plan = model._plan(eng, H, W)
+    handle = model._device_model()
+    dev = eng.upload_images(frames)
+    chns = eng.pyramid(dev, plan)
+    hit_cap = eng.default_hit_cap(plan, B)
+
+    def step_device():
+        eng.pyramid(dev, plan, out=chns)
+        return eng.cascade_launch(handle, plan, chns, B, hit_cap)
+
+    def read_counts(meta, nbytes):
+        n_hits, stats, _ = eng._read_meta(meta, nbytes, B, plan.n_levels)
+        return n_hits, int(stats[:, 0].sum()), int(stats[:, 1].sum())
+
+    # ---- device-resident throughput: `value`
+    for _ in range(max(args.warmup, 3)):
+        _, meta, nbytes = step_device()
+    n_hits, n_loc, n_weak = read_counts(meta, nbytes)
+    assert n_hits <= hit_cap
+    barrier()
+    eng.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            step_device()
+        ev1.record()
+        barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    frames_total = B * args.steps * world
+    value = frames_total / (ms_total * 1e-3)
+
+    # ---- end to end through the public API: pinned host frames in, boxes out
+    for _ in range(2):
+        model.detect_batch(frames)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, hits = model.detect_batch(frames, return_hits=True)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": frames_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
+           "d2h_bytes_per_step": int(hits.nbytes + 8 + 16 * B + 4 * B * plan.n_levels)}
+
+    # ---- roofline of the two dominant kernels (algorithmic bytes per launch / CUDA-event time per launch)
+    peaks, peak_src = {}, "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    pyr_b, cas_b = algorithmic_bytes(plan, 1, n_hits / B)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+
+    def roof(kind, bytes_per_frame, name):
+        ms, n = prof[kind]
+        if n == 0:
+            return None
+        per_launch_s = ms * 1e-3 / n
+        ach = bytes_per_frame * B / per_launch_s / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(name), "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
+                "ms_per_launch": per_launch_s * 1e3, "peak_source": peak_src,
+                "share_of_step": ms / n / (ms_total / args.steps)}
+
+    r_pyr = roof("level_kernel", pyr_b, "level_kernel")
+    r_cas = roof("cascade_kernel", cas_b, "cascade_kernel")
+    dominant = r_cas if (r_cas and r_pyr and r_cas["ms_per_launch"] > r_pyr["ms_per_launch"]) else (r_pyr or r_cas)
+
+    launches_per_step = 2 + (plan.info.n_octaves - 1) + 1 + 4   # minmax_init, minmax, octaves, level | cascade, 2 scans, emit
+    n_weak_all = sum_over_ranks(float(n_weak))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch of {B} synthetic 1920x1080 uint8 frames per GPU, 12x12x4 grad_hist model "
+                                   f"(shrink 2, n_per_oct 8, smooth 1), 1024 depth-2 stages, {args.profile} thetas "
+                                   "(BASELINE configs[1]; image-sharded over GPUs = configs[4])",
+                       "profile": args.profile, "batch_per_gpu": B, "unique_frames_per_gpu": uniq,
+                       "levels": plan.n_levels, "windows_per_frame": int(plan.info.n_loc),
+                       "eval_cost": n_weak / max(n_loc, 1), "hits_per_frame": n_hits / B,
+                       "window_stage_evals_per_s": n_weak_all * args.steps / (ms_total * 1e-3),
+                       "l2": f"inputs larger than L2: {frames.nbytes / 1e6:.0f} MB of frames and {chns.numel() * 4 / 1e9:.2f} GB of channels per step",
+                       "parallelism": f"image-sharded x{world}, no collective"},
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": dominant, "roofline_pyramid": r_pyr, "roofline_cascade": r_cas,
+            "cpu_baseline": cpu, "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--unique-frames", type=int, default=16, help="distinct synthetic frames per GPU (cycled to fill the batch)")
+    ap.add_argument("--profile", choices=["wald", "dense"], default="wald")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--cpu-workers", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,14 @@ int wbg_cascade_trace(const wbg_model* model, const float* X, int32_t u, int32_t
 int wbg_gather_samples(const float* X, int32_t u, int32_t v, int32_t c, const int32_t* rs, const int32_t* cs,
                        int64_t K, int32_t m, int32_t n, float* out, void* stream);
 
+/* ---- measurement aid (bench.py): while enabled, the library brackets its two dominant kernels -- the fused
+ * per-level channel kernel and the cascade kernel -- with CUDA events on the caller's stream.  wbg_profile_read
+ * waits for the recorded events, returns the accumulated kernel time (ms) and launch count per kind since the last
+ * read, and clears them.  Not thread-safe; meant for one stream. */
+enum { WBG_PROF_LEVEL_KERNEL = 0, WBG_PROF_CASCADE_KERNEL = 1, WBG_PROF_KINDS = 2 };
+int wbg_profile_enable(int32_t on);
+int wbg_profile_read(double* ms /* [WBG_PROF_KINDS] */, int64_t* launches /* [WBG_PROF_KINDS] */);
+
 #ifdef __cplusplus
 }
 #endif

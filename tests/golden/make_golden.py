@@ -43,14 +43,20 @@ def ref_model(shape, opts, trees, thetas):
     return M
 
 
-def calibrate(M, chns_list, T, keep_total):
-    """wald thetas from the reference's own DTree.predict_on_image over all windows of the given maps."""
+def calibrate(M, chns_list, T, keep_total, subsample=None, seed=0):
+    """wald thetas from the reference's own DTree.predict_on_image over all windows of the given maps
+    (or a seeded random fraction `subsample` of them)."""
     m, n, _ = M.shape
     maps, R, Cc = [], [], []
+    rng = np.random.default_rng(seed)
     for k, X in enumerate(chns_list):
         u, v, _ = X.shape
         rs, cs = np.indices((max(u - m, 0), max(v - n, 0)))
-        maps.append(np.full(rs.size, k)); R.append(rs.ravel()); Cc.append(cs.ravel())
+        rs, cs = rs.ravel(), cs.ravel()
+        if subsample is not None:
+            pick = rng.random(rs.size) < subsample
+            rs, cs = rs[pick], cs[pick]
+        maps.append(np.full(rs.size, k)); R.append(rs); Cc.append(cs)
     mp, R, Cc = np.concatenate(maps), np.concatenate(R), np.concatenate(Cc)
 
     def stage(t, alive):
@@ -76,7 +82,35 @@ def detect_record(M, image):
     return levels, dt.get(), dt.get_field("scores"), n_loc, n_weak
 
 
+def config_B():
+    """BASELINE config B / E model: 12x12x4 grad_hist, 1024 depth-2 stages, 'wald' thetas calibrated with the
+    reference on a seeded 8 % sample of the windows of all levels of the 1080p frames seed 1000..1003 (SURVEY.md 8d
+    calibrates on frame 1000 only; four frames make the thresholds robust to the frames' different noise amplitudes) -> configB_model.pb (used by bench.py), plus the
+    reference's detect() output on a 540x960 crop of that frame (a 1080p reference run costs minutes)."""
+    shape = (12, 12, 4)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=rch.grad_hist)
+    frame = S.synthetic_frame(1000, 1080, 1920)
+    lv = []
+    for seed in range(1000, 1004):
+        lv += [c for c, _ in rch.channel_pyramid(S.synthetic_frame(seed, 1080, 1920), opts) if c.shape[0] > 12 and c.shape[1] > 12]
+    first = [c for c in lv if c.shape[:2] == (540, 960)]
+    lo, hi = S.channel_quantiles(np.concatenate([c.reshape(-1, 4) for c in first])[None])
+    trees = S.random_trees(shape, 1024, 2, lo, hi, seed=7)
+    M = ref_model(shape, opts, trees, [-np.inf] * 1024)
+    th = calibrate(M, lv, 1024, 1e-4, subsample=0.08, seed=1)
+    M.theta = [float(x) for x in th]
+    M.save(os.path.join(HERE, "configB_model.pb"))
+    M = RModel.load(os.path.join(HERE, "configB_model.pb"))
+    crop = np.ascontiguousarray(frame[270:810, 480:1440])
+    levels, boxes, scores, n_loc, n_weak = detect_record(M, crop)
+    np.savez_compressed(os.path.join(HERE, "configB_detect.npz"), boxes=boxes, scores=scores, n_loc=np.int64(n_loc),
+                        n_weak=np.int64(n_weak), level_counts=np.array([r.size for r, *_ in levels]))
+    print("config B (540x960 crop): hits", scores.size, "n_loc", n_loc, "n_weak", n_weak, "eval_cost", n_weak / n_loc)
+
+
 def main():
+    if "--config-b" in sys.argv:
+        return config_B()
     # ---------------------------------------------------------------- small pyramid fixtures
     frame = S.synthetic_frame(1000, 96, 128)
     frame_f = frame.astype(np.float32) + np.random.default_rng(5).random(frame.shape).astype(np.float32)

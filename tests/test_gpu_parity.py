@@ -1,0 +1,363 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path behind the C ABI against (1) golden outputs of the
+unmodified reference (tests/golden/) and (2) the oracle (oracle/wb_oracle.py) on the same seeded inputs.
+
+Bars: channels |d| <= 1e-5 * max(|ref|, 1); given identical channels the leaf indices, survivor sets,
+n_loc / n_weak and float32 scores are bit-exact; boxes bit-exact given identical (r, c, scale)."""
+import functools
+import os
+
+import numpy as np
+import pytest
+
+import wb_oracle as O
+import waldboost_b200 as wb
+from waldboost_b200 import synthetic as S
+from helpers import GOLDEN, calibrate_on_oracle, channels_close, make_model, oracle_cascade, oracle_opts
+
+pytestmark = pytest.mark.gpu
+
+CH = wb.channels
+CFG = {
+    "hist4_s2_sm1": dict(shrink=2, n_per_oct=4, smooth=1, channels=CH.grad_hist),
+    "hist4_s1_sm0": dict(shrink=1, n_per_oct=2, smooth=0, channels=CH.grad_hist),
+    "mag_s2_sm1": dict(shrink=2, n_per_oct=3, smooth=1, channels=CH.grad_mag),
+    "hist6full_s2_sm1": dict(shrink=2, n_per_oct=2, smooth=1,
+                             channels=functools.partial(CH.grad_hist, n_bins=6, full=True, bias=2)),
+}
+OPTS_A = dict(shrink=2, n_per_oct=8, smooth=1, channels=CH.grad_hist)
+
+
+def assert_pyramid_close(got_levels, ref_levels, exact_scale=True):
+    assert len(got_levels) == len(ref_levels)
+    n_px = n_inexact = 0
+    for k, ((g, gs), (r, rs)) in enumerate(zip(got_levels, ref_levels)):
+        ok, bad, worst, inexact = channels_close(g, r)
+        assert ok, f"level {k} {g.shape}: {bad} values outside 1e-5 rel (worst ratio {worst:.3g})"
+        if exact_scale:
+            assert gs == rs, f"level {k}: scale {gs} != {rs}"
+        n_px += r.size
+        n_inexact += inexact
+    return n_px, n_inexact
+
+
+# ------------------------------------------------------------------------------------------- channel pyramid
+@pytest.mark.parametrize("name", list(CFG))
+@pytest.mark.parametrize("tag", ["u8", "f32"])
+def test_pyramid_vs_reference_golden(name, tag):
+    """every level of channel_pyramid on the 96x128 fixture against arrays produced by the unmodified reference."""
+    g = np.load(os.path.join(GOLDEN, "small_pyramid.npz"))
+    img = g["frame_" + tag]
+    n_ref = len([k for k in g.files if k.startswith(f"{name}/{tag}/") and k.endswith("/scale")])
+    ref = [(g[f"{name}/{tag}/{k}"], float(g[f"{name}/{tag}/{k}/scale"])) for k in range(n_ref)]
+    got = list(CH.channel_pyramid(img, CFG[name]))
+    assert_pyramid_close(got, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("size", [(480, 640), (1080, 1920), (135, 241), (67, 120), (9, 8), (300, 17)])
+def test_pyramid_vs_oracle_sizes(dtype, size):
+    """config A/B geometries plus odd, tiny and thin frames (levels far smaller than a tile, multi-wrap reflect)."""
+    H, W = size
+    img = S.synthetic_frame(1000, H, W).astype(dtype)
+    if dtype == np.float32:
+        img = img + np.random.default_rng(3).random(img.shape).astype(np.float32)
+    ref = list(O.channel_pyramid(img, oracle_opts(OPTS_A)))
+    got = list(CH.channel_pyramid(img, OPTS_A))
+    n_px, n_inexact = assert_pyramid_close(got, ref)
+    # integer-valued gradients make the uint8 path exact up to the float64 -> float32 roundings both sides share
+    assert n_inexact <= 1e-3 * n_px, f"{n_inexact} of {n_px} channel values are not bit-identical"
+
+
+def test_pyramid_noise_frame_and_mag_hist():
+    """config C's 10-channel feature (grad_mag(norm=5) + grad_hist(9)) on a pure-noise frame."""
+    img = S.noise_frame(5, 270, 480)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=CH.grad_mag_hist)
+    ref = list(O.channel_pyramid(img, oracle_opts(opts)))
+    got = list(CH.channel_pyramid(img, opts))
+    assert got[0][0].shape[2] == 10
+    assert_pyramid_close(got, ref)
+
+
+@pytest.mark.parametrize("norm", [None, 1, 2, 5, 8])
+def test_grad_mag_norms(norm):
+    img = S.synthetic_frame(1001, 50, 70)
+    opts = dict(shrink=1, n_per_oct=2, smooth=0, channels=functools.partial(CH.grad_mag, norm=norm))
+    assert_pyramid_close(list(CH.channel_pyramid(img, opts)), list(O.channel_pyramid(img, oracle_opts(opts))))
+
+
+def test_channel_functions_direct():
+    """wb.channels.grad_hist(image) / grad_mag(image) called on an image like the reference functions."""
+    img = S.synthetic_frame(1002, 61, 83)
+    for got, ref in ((CH.grad_hist(img), O.grad_hist(img)), (CH.grad_hist(img, 6, True, 1.5), O.grad_hist(img, 6, True, 1.5)),
+                     (CH.grad_mag(img), O.grad_mag(img)), (CH.grad_mag_hist(img), O.grad_mag_hist(img))):
+        assert channels_close(got, ref)[0]
+    tiny = S.noise_frame(1, 5, 6)        # below the 8-pixel octave cut-off: still a valid direct call
+    assert channels_close(CH.grad_hist(tiny), O.grad_hist(tiny))[0]
+
+
+def test_primitives():
+    rng = np.random.default_rng(9)
+    x = (rng.random((21, 18, 4)) * 100).astype(np.float32)
+    assert np.array_equal(CH.avg_pool_2(x), O.avg_pool_2(x))
+    assert np.array_equal(CH.max_pool_2(x), O.max_pool_2(x))
+    assert np.array_equal(CH.smooth_image_3d(x), O.smooth_image_3d(x))
+    x2 = (rng.random((7, 9)) * 10).astype(np.float32)
+    assert np.array_equal(CH.avg_pool_2(x2), O.avg_pool_2(x2))
+    assert not CH.smooth_image_3d(np.ones((2, 4, 3), np.float32)).any()
+    assert CH.avg_pool_2(np.ones((1, 9, 2), np.float32)).shape == (0, 4, 2)
+
+
+def test_pyramid_errors():
+    with pytest.raises(TypeError):
+        list(CH.channel_pyramid([[1, 2], [3, 4]], OPTS_A))
+    with pytest.raises(ValueError):
+        list(CH.channel_pyramid(np.zeros((4, 4, 3), np.uint8), OPTS_A))
+    with pytest.raises(AssertionError):
+        list(CH.channel_pyramid(np.zeros((32, 32), np.uint8), dict(OPTS_A, shrink=3)))
+    with pytest.raises(TypeError):                       # arbitrary callables have no CUDA implementation
+        list(CH.channel_pyramid(np.zeros((32, 32), np.uint8), dict(OPTS_A, channels=lambda im: im[..., None])))
+    with pytest.raises(TypeError):
+        list(CH.channel_pyramid(np.zeros((32, 32), np.float64), OPTS_A))
+    assert list(CH.channel_pyramid(np.zeros((7, 100), np.uint8), OPTS_A)) == []      # below the octave cut-off
+
+
+# ------------------------------------------------------------------------------------------- cascade on oracle channels
+def _oracle_levels(frame, opts):
+    return list(O.channel_pyramid(frame, oracle_opts(opts)))
+
+
+@pytest.mark.parametrize("depth,stages", [(2, 64), (1, 16), (3, 24), (4, 40)])
+@pytest.mark.parametrize("profile", ["dense", "wald"])
+def test_cascade_on_oracle_channels(depth, stages, profile):
+    """given identical channels: survivor sets, float32 scores, n_loc, n_weak bit-exact (facts 1, 7, 8)."""
+    frame = S.synthetic_frame(1000, 200, 260)
+    M = make_model((12, 12, 4), OPTS_A, stages, depth, frame, seed=depth, keep_total=1e-3 if profile == "wald" else None)
+    Cs = oracle_cascade(M)
+    for X, _ in _oracle_levels(frame, OPTS_A)[::3]:
+        r, c, h = M.predict_on_image(X)
+        ro, co, ho = Cs.predict_on_image(X)
+        assert r.dtype == np.int64 and h.dtype == np.float32
+        assert np.array_equal(r, ro) and np.array_equal(c, co)
+        assert np.array_equal(h, ho)
+    assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak) and M.n_loc > 0
+    assert M.eval_cost == Cs.eval_cost
+
+
+def test_leaf_indices_bit_exact():
+    """stage-wise leaf index of every window (training.py:84-95) for full, unbalanced and stump trees."""
+    frame = S.synthetic_frame(1000, 96, 128)
+    M = wb.Model.load(os.path.join(GOLDEN, "generic_model.pb"))
+    Cs = oracle_cascade(M)
+    X = _oracle_levels(frame, M.channel_opts)[0][0]
+    u, v, _ = X.shape
+    rs, cs = (a.ravel() for a in np.indices((u - 12, v - 12)))
+    leaf, score = M.trace_windows(X, rs, cs)
+    hs = np.zeros(rs.size, np.float32)
+    for t, tree in enumerate(Cs.classifier):
+        ref_leaf = tree.leaf_on_image(X, rs, cs)
+        assert np.array_equal(leaf[:, t], ref_leaf), f"stage {t}"
+        hs += tree.prediction[ref_leaf]
+    assert np.array_equal(score, hs)
+    # one tree on its own: DTree.predict_on_image
+    t0 = M.classifier[3]
+    assert np.array_equal(t0.predict_on_image(X, rs, cs), Cs.classifier[3].predict_on_image(X, rs, cs))
+
+
+def test_cascade_edge_cases():
+    rng = np.random.default_rng(2)
+    frame = S.synthetic_frame(1000, 96, 128)
+    M = make_model((12, 12, 4), OPTS_A, 8, 2, frame)
+    # maps not larger than the window: the grid (u-m) x (v-n) is empty (fact 1: u == m gives NO window)
+    for shape in [(12, 12, 4), (12, 40, 4), (5, 7, 4), (13, 12, 4)]:
+        r, c, h = M.predict_on_image(rng.random(shape).astype(np.float32))
+        assert r.size == c.size == h.size == 0
+    X = (rng.random((13, 13, 4)) * 50).astype(np.float32)          # exactly one window
+    r, c, h = M.predict_on_image(X)
+    ro, co, ho = oracle_cascade(M).predict_on_image(X)
+    assert r.tolist() == [0] and c.tolist() == [0] and np.array_equal(h, ho)
+    with pytest.raises(AssertionError):                                # model.py:238
+        M.predict_on_image(np.zeros((30, 30, 3), np.float32))
+    # no stages: every window survives with score 0 (the loop body never runs)
+    E = wb.Model((12, 12, 4), OPTS_A)
+    r, c, h = E.predict_on_image(np.zeros((20, 25, 4), np.float32))
+    assert r.size == 8 * 13 and not h.any() and E.n_loc == 104 and E.n_weak == 0
+    # everything rejected at the first stage
+    M.theta = [np.inf] + [-np.inf] * 7
+    M.reset()
+    r, c, h = M.predict_on_image((rng.random((40, 40, 4)) * 50).astype(np.float32))
+    assert r.size == 0 and M.n_loc == 28 * 28 and M.n_weak == 28 * 28     # one stage evaluated, then the break
+    # NaN channels go right (x <= thr is False); the scores stay finite (sums of leaf predictions)
+    M.theta = [-np.inf] * 8
+    Xn = np.full((20, 20, 4), np.nan, np.float32)
+    ro, co, ho = oracle_cascade(M).predict_on_image(Xn)
+    r, c, h = M.predict_on_image(Xn)
+    assert np.array_equal(r, ro) and np.array_equal(h, ho, equal_nan=True) and r.size == 64
+    M.theta = [-np.inf] * 7 + [float(ho[0])]
+    assert M.predict_on_image(Xn)[0].size == 64 == oracle_cascade(M).predict_on_image(Xn)[0].size
+    M.theta = [-np.inf] * 7 + [float(np.nextafter(ho[0], np.float32(np.inf)))]
+    assert M.predict_on_image(Xn)[0].size == 0 == oracle_cascade(M).predict_on_image(Xn)[0].size
+
+
+def test_hit_capacity_overflow_reruns():
+    """WBG_ECAP semantics: more survivors than the hit buffer -> n_hits reports the true count and the host re-runs."""
+    from waldboost_b200.engine import get_engine
+    frame = S.synthetic_frame(1000, 96, 128)
+    M = make_model((12, 12, 4), OPTS_A, 4, 2, frame)
+    X = _oracle_levels(frame, OPTS_A)[0][0]
+    ro, co, ho = oracle_cascade(M).predict_on_image(X)
+    hits, stats = get_engine().predict_on_map(M._device_model(), X, hit_cap=7)
+    assert hits.size == ro.size > 7 and np.array_equal(hits["score"], ho) and np.array_equal(hits["r"], ro)
+
+
+def test_large_window_and_many_channels():
+    """20x20x10 window of config C (generic smem geometry) on oracle channels."""
+    img = S.synthetic_frame(1003, 180, 240)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=CH.grad_mag_hist)
+    M = make_model((20, 20, 10), opts, 32, 2, img, keep_total=1e-2)
+    Cs = oracle_cascade(M)
+    for X, _ in _oracle_levels(img, opts)[:6:2]:
+        r, c, h = M.predict_on_image(X)
+        ro, co, ho = Cs.predict_on_image(X)
+        assert np.array_equal(r, ro) and np.array_equal(c, co) and np.array_equal(h, ho)
+    assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak)
+
+
+def test_gather_samples():
+    from waldboost_b200.engine import get_engine
+    rng = np.random.default_rng(4)
+    X = rng.random((40, 50, 4)).astype(np.float32)
+    rs, cs = rng.integers(0, 28, 33), rng.integers(0, 38, 33)
+    got = get_engine().gather_samples(X, rs, cs, (12, 12, 4))
+    assert np.array_equal(got, O.gather_samples(X, rs, cs, (12, 12, 4)))
+
+
+# ------------------------------------------------------------------------------------------- detect(): end to end
+def _key_hits(levels, r, c):
+    return set(zip(levels.tolist(), r.tolist(), c.tolist()))
+
+
+def _agreement(got_hits, ref_levels, ref_r, ref_c, ref_h, tol=1e-4):
+    """matched on (level, r, c) with |dscore| <= tol, over the union."""
+    ref = {(int(l), int(r), int(c)): float(h) for l, r, c, h in zip(ref_levels, ref_r, ref_c, ref_h)}
+    got = {(int(h["level"]), int(h["r"]), int(h["c"])): float(h["score"]) for h in got_hits}
+    union = set(ref) | set(got)
+    good = sum(1 for k in union if k in ref and k in got and abs(ref[k] - got[k]) <= tol)
+    return good / max(len(union), 1), len(union)
+
+
+@pytest.mark.parametrize("prof", ["wald", "dense"])
+def test_detect_vs_reference_golden_small(prof):
+    g = np.load(os.path.join(GOLDEN, "small_detect.npz"))
+    frame = np.load(os.path.join(GOLDEN, "small_pyramid.npz"))["frame_u8"]
+    M = wb.Model.load(os.path.join(GOLDEN, "small_model.pb"))
+    if prof == "dense":
+        M.theta = [-np.inf] * len(M)
+    dt = M.detect(frame)
+    assert isinstance(dt, wb.Boxes) and dt.has_field("scores")
+    assert np.array_equal(dt.get(), g[f"{prof}/boxes"])
+    assert np.array_equal(dt.get_field("scores"), g[f"{prof}/scores"])
+    assert (M.n_loc, M.n_weak) == (int(g[f"{prof}/n_loc"]), int(g[f"{prof}/n_weak"]))
+    M.reset()
+    for k, (chns, scale, (r, c, h)) in enumerate(M.scan_channels(frame)):
+        assert np.array_equal(r, g[f"{prof}/{k}/r"]) and np.array_equal(c, g[f"{prof}/{k}/c"])
+        assert np.array_equal(h, g[f"{prof}/{k}/h"])
+        assert np.array_equal(M.get_boxes(r, c, scale).get(), oracle_cascade(M).get_boxes(r, c, scale))
+
+
+def test_detect_vs_reference_golden_generic_topology():
+    g = np.load(os.path.join(GOLDEN, "generic_detect.npz"))
+    frame = np.load(os.path.join(GOLDEN, "small_pyramid.npz"))["frame_u8"]
+    M = wb.Model.load(os.path.join(GOLDEN, "generic_model.pb"))
+    dt = M.detect(frame)
+    assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+    assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
+
+
+def test_detect_config_A_vs_reference_golden():
+    """BASELINE config A: 640x480, 12x12x4, 256 depth-2 stages -- the reference's own detect() output."""
+    g = np.load(os.path.join(GOLDEN, "configA_detect.npz"))
+    M = wb.Model.load(os.path.join(GOLDEN, "configA_model.pb"))
+    frame = S.synthetic_frame(1000, 480, 640)
+    dt = M.detect(frame)
+    assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+    assert M.n_loc == int(g["n_loc"]) == 407350 and M.n_weak == int(g["n_weak"])
+    sums = [c.astype(np.float64).sum() for c, _ in M.channels(frame)]
+    assert np.allclose(sums, g["level_sums"], rtol=1e-7)
+
+
+def test_detect_batch_equals_per_frame_and_oracle():
+    """image-sharded batch (config B's shape at reduced size): batch result == frame-by-frame result == oracle."""
+    frames = S.synthetic_frames(5, 240, 320)
+    M = make_model((12, 12, 4), OPTS_A, 48, 2, frames[0], keep_total=1e-3, calib_levels=2)
+    Cs = oracle_cascade(M)
+    M.reset()
+    out, hits = M.detect_batch(frames, return_hits=True)
+    stats_batch = (M.n_loc, M.n_weak)
+    assert len(out) == 5 and np.all(np.diff(hits["frame"]) >= 0)
+    total = 0
+    for b in range(5):
+        ob, os_, ol = Cs.detect(frames[b])
+        one = M.detect(frames[b])
+        assert np.array_equal(one.get(), out[b].get()) and np.array_equal(one.get_field("scores"), out[b].get_field("scores"))
+        assert np.array_equal(out[b].get(), ob) and np.array_equal(out[b].get_field("scores"), os_)
+        assert np.array_equal(hits["level"][hits["frame"] == b], ol)
+        total += os_.size
+    assert total > 0 and (Cs.n_loc, Cs.n_weak) == stats_batch
+
+
+def test_detect_1080p_noise_agreement():
+    """config B geometry (one 1080p frame, 1024 depth-2 stages), worst-case input; SURVEY.md 8d agreement >= 95 %."""
+    frame = S.noise_frame(11, 1080, 1920)
+    small = S.noise_frame(12, 270, 480)
+    M = make_model((12, 12, 4), OPTS_A, 1024, 2, small)
+    # strong rejection over the first 64 stages (so the oracle finishes in seconds), none over the other 960
+    head = wb.Model((12, 12, 4), OPTS_A)
+    for w in M.classifier[:64]:
+        head.append(w, -np.inf)
+    th = calibrate_on_oracle(head, [O.channel_pyramid(small, oracle_opts(OPTS_A)).__next__()[0]], 1e-3)
+    M.theta = [float(x) for x in th] + [-np.inf] * 960
+    Cs = oracle_cascade(M)
+    _, hits = M.detect_batch(frame[None], return_hits=True)
+    rl, rr, rc, rh = [], [], [], []
+    for lvl, (chns, scale, (r, c, h)) in enumerate(Cs.scan_channels(frame)):
+        rl.append(np.full(r.size, lvl)); rr.append(r); rc.append(c); rh.append(h)
+    agree, n = _agreement(hits, np.concatenate(rl), np.concatenate(rr), np.concatenate(rc), np.concatenate(rh))
+    assert agree >= 0.95, f"agreement {agree:.4f} over {n} hits"
+    assert M.n_loc == Cs.n_loc == 3045278
+
+
+def test_multi_model_detect_shared_pyramid():
+    frame = S.synthetic_frame(1000, 200, 260)
+    A = make_model((12, 12, 4), OPTS_A, 16, 2, frame, seed=1, keep_total=1e-2)
+    B = make_model((16, 10, 4), OPTS_A, 16, 2, frame, seed=2, keep_total=1e-2)
+    dt = wb.detect(frame, A, B, response_scale=[1.0, 0.5])
+    lab = dt.get_field("label")
+    a, b = A.detect(frame), B.detect(frame)
+    assert (lab == 0).sum() == len(a) and (lab == 1).sum() == len(b) and len(a) and len(b)
+    assert np.array_equal(np.sort(dt.get_field("scores")[lab == 0]), np.sort(a.get_field("scores")))
+    assert np.array_equal(np.sort(dt.get_field("scores")[lab == 1]), np.sort(b.get_field("scores") * np.float32(0.5)))
+
+
+def test_model_mutation_resyncs_device_copy():
+    frame = S.synthetic_frame(1000, 96, 128)
+    M = make_model((12, 12, 4), OPTS_A, 12, 2, frame)
+    n_dense = len(M.detect(frame))
+    M.theta = [0.0] * 12                       # reference scripts assign model.theta directly
+    n_tight = len(M.detect(frame))
+    Cs = oracle_cascade(M)
+    assert n_tight == Cs.detect(frame)[1].size < n_dense
+    M.channel_opts["n_per_oct"] = 4            # and mutate channel_opts (scripts/waldboost-detect.py:55)
+    Cs = oracle_cascade(M)
+    assert len(M.detect(frame)) == Cs.detect(frame)[1].size
+
+
+def test_detect_config_B_model_vs_reference_golden():
+    """BASELINE config B model (1024 depth-2 stages, wald thetas, the one bench.py times) on a 540x960 crop of frame
+    1000: the reference's own detect() output, bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "configB_detect.npz"))
+    M = wb.Model.load(os.path.join(GOLDEN, "configB_model.pb"))
+    assert len(M) == 1024
+    crop = np.ascontiguousarray(S.synthetic_frame(1000, 1080, 1920)[270:810, 480:1440])
+    dt = M.detect(crop)
+    assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
+    assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])

@@ -70,7 +70,10 @@ SYMBOLS = {
     "wbg_predict_on_image": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _SZ, _P]),
     "wbg_cascade_trace": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _P, _P, _P]),
     "wbg_gather_samples": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P, _P]),
+    "wbg_profile_enable": (C.c_int, [_I32]),
+    "wbg_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_I64)]),
 }
+PROF_KINDS = ("level_kernel", "cascade_kernel")
 
 
 class WbgError(RuntimeError):

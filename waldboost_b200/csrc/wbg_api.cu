@@ -30,6 +30,50 @@ extern "C" int wbg_device_count(void) {
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------ profiling hooks
+struct ProfSpan { int kind; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof_spans;
+static cudaEvent_t g_prof_open[WBG_PROF_KINDS];
+
+void wbg_prof_begin(int kind, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    g_prof_open[kind] = e;
+}
+
+void wbg_prof_end(int kind, cudaStream_t stream) {
+    if (!g_prof_on || !g_prof_open[kind]) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    g_prof_spans.push_back({kind, g_prof_open[kind], e});
+    g_prof_open[kind] = nullptr;
+}
+
+extern "C" int wbg_profile_enable(int32_t on) {
+    g_prof_on = on != 0;
+    return WBG_OK;
+}
+
+extern "C" int wbg_profile_read(double* ms, int64_t* launches) {
+    WBG_REQUIRE(ms && launches, "wbg_profile_read: null argument");
+    for (int k = 0; k < WBG_PROF_KINDS; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    for (auto& s : g_prof_spans) {
+        float t = 0.f;
+        WBG_CUDA_TRY(cudaEventSynchronize(s.b));
+        WBG_CUDA_TRY(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.kind] += (double)t;
+        launches[s.kind] += 1;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    g_prof_spans.clear();
+    return WBG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ geometry
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
     // Largest tile whose planar channel patch + window lists fit a budget that keeps >= 2 CTAs per SM.

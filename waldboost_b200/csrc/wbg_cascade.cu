@@ -413,11 +413,14 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     if (model->all_d2) {
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
         WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);
         cascade_kernel<true><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
     } else {
         WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);
         cascade_kernel<false><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
     }
+    wbg_prof_end(WBG_PROF_CASCADE_KERNEL, stream);
     WBG_CUDA_TRY(cudaGetLastError());
 
     mask_block_sums<<<w.n_blocks, SCAN_THREADS, 0, stream>>>(w.mask, w.block_sums);

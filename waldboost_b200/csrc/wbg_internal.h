@@ -113,6 +113,10 @@ struct wbg_model {
     StageD2* d_d2 = nullptr;      // [T] when all_d2
 };
 
+// ------------------------------------------------------------------------------------------------ profiling hooks
+void wbg_prof_begin(int kind, cudaStream_t stream);
+void wbg_prof_end(int kind, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------ launchers
 int wbg_launch_pyramid(const wbg_plan* plan, const void* img, int dtype, int batch, float* chns, void* ws,
                        size_t ws_bytes, cudaStream_t stream);

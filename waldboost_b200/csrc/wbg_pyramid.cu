@@ -390,7 +390,9 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
     WBG_CUDA_TRY(cudaFuncSetAttribute(level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)plan->ptiles * batch;
     WBG_REQUIRE(grid <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid);
+    wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);
     level_kernel<T><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);
+    wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);
     WBG_CUDA_TRY(cudaGetLastError());
     return WBG_OK;
 }

@@ -195,16 +195,21 @@ class Engine:
         raise TypeError(f"image dtype {dtype} is not supported on the GPU path (uint8 and float32 only; no CPU fallback)")
 
     def upload_images(self, images):
-        """numpy [B,H,W] (uint8 / float32) -> device tensor through a cached pinned staging buffer."""
+        """numpy [B,H,W] (uint8 / float32) -> device tensor.  Page-locked input (e.g. a NumPy view of a pinned torch
+        tensor) is copied straight to the device; pageable input goes through a cached pinned staging buffer."""
         torch = self.torch
         images = np.ascontiguousarray(images)
         self.image_dtype(images.dtype)
         nbytes = images.nbytes
+        tdt = torch.uint8 if images.dtype == np.uint8 else torch.float32
+        dev = self.buffer("img", nbytes)[:nbytes].view(tdt).view(images.shape)
+        src = torch.from_numpy(images) if images.flags.writeable else None
+        if src is not None and src.is_pinned():
+            dev.copy_(src, non_blocking=True)
+            return dev
         stage = self.pinned("img", nbytes)
         stage_np = stage.numpy()[:nbytes].view(images.dtype).reshape(images.shape)
         np.copyto(stage_np, images)
-        tdt = torch.uint8 if images.dtype == np.uint8 else torch.float32
-        dev = self.buffer("img", nbytes)[:nbytes].view(tdt).view(images.shape)
         dev.copy_(stage[:nbytes].view(tdt).view(images.shape), non_blocking=True)
         return dev
 
@@ -271,24 +276,32 @@ class Engine:
         self.torch.cuda.current_stream(self.device).synchronize()
         return host.numpy()[:nb].view(N.HIT_DTYPE).copy()
 
+    def cascade_launch(self, model_handle, plan, chns, B, hit_cap):
+        """Enqueue the cascade over every level of B frames on the current stream (no synchronisation).
+        Returns (hits device buffer, meta device buffer, meta bytes)."""
+        lib = self.lib
+        ws = self.buffer("cas_ws", lib.wbg_cascade_workspace_bytes(plan.handle, B))
+        hits_t = self.buffer("hits", hit_cap * N.HIT_DTYPE.itemsize)
+        meta, nbytes, p_nhits, p_stats, p_counts = self._meta(B, plan.n_levels)
+        with self.torch.cuda.device(self.device):
+            code = lib.wbg_cascade_scan(model_handle.handle, plan.handle, C.c_void_p(chns.data_ptr()), B,
+                                        C.c_void_p(hits_t.data_ptr()), hit_cap, C.c_void_p(p_counts),
+                                        C.c_void_p(p_stats), C.c_void_p(p_nhits), C.c_void_p(ws.data_ptr()),
+                                        ws.numel(), self._stream())
+        if code == N.WBG_EINVAL and "Invalid number of channels" in N.last_error():
+            raise AssertionError(N.last_error())       # reference model.py:238 is an assert
+        N.check(code)
+        return hits_t, meta, nbytes
+
+    def default_hit_cap(self, plan, B):
+        return int(min(max(plan.info.n_loc * B, 1), 1 << 20))
+
     def cascade(self, model_handle, plan, chns, B, hit_cap=None):
         """Run the cascade over every level of B frames.  Returns (hits, level_counts [B,L], stats [B,2])."""
-        lib = self.lib
         if hit_cap is None:
-            hit_cap = int(min(max(plan.info.n_loc * B, 1), 1 << 20))
-        wsb = lib.wbg_cascade_workspace_bytes(plan.handle, B)
-        ws = self.buffer("cas_ws", wsb)
+            hit_cap = self.default_hit_cap(plan, B)
         while True:
-            hits_t = self.buffer("hits", hit_cap * N.HIT_DTYPE.itemsize)
-            meta, nbytes, p_nhits, p_stats, p_counts = self._meta(B, plan.n_levels)
-            with self.torch.cuda.device(self.device):
-                code = lib.wbg_cascade_scan(model_handle.handle, plan.handle, C.c_void_p(chns.data_ptr()), B,
-                                            C.c_void_p(hits_t.data_ptr()), hit_cap, C.c_void_p(p_counts),
-                                            C.c_void_p(p_stats), C.c_void_p(p_nhits), C.c_void_p(ws.data_ptr()),
-                                            ws.numel(), self._stream())
-            if code == N.WBG_EINVAL and "Invalid number of channels" in N.last_error():
-                raise AssertionError(N.last_error())       # reference model.py:238 is an assert
-            N.check(code)
+            hits_t, meta, nbytes = self.cascade_launch(model_handle, plan, chns, B, hit_cap)
             n_hits, stats, counts = self._read_meta(meta, nbytes, B, plan.n_levels)
             if n_hits <= hit_cap:
                 return self._read_hits(hits_t, n_hits), counts, stats
@@ -349,6 +362,17 @@ class Engine:
                                                 C.c_void_p(rs_d.data_ptr()), C.c_void_p(cs_d.data_ptr()), K, m, n,
                                                 C.c_void_p(out.data_ptr()), self._stream()))
         return out.cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------- measurement
+    def profile_enable(self, on):
+        N.check(self.lib.wbg_profile_enable(1 if on else 0))
+
+    def profile_read(self):
+        """{kind: (kernel ms since the last read, launches)} from the library's CUDA-event brackets."""
+        ms = (C.c_double * len(N.PROF_KINDS))()
+        n = (C.c_int64 * len(N.PROF_KINDS))()
+        N.check(self.lib.wbg_profile_read(ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(N.PROF_KINDS)}
 
     def map_primitive(self, fn_name, arr, out_shape):
         torch = self.torch

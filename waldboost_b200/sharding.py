@@ -1,0 +1,78 @@
+"""Multi-GPU partitioning of the detect() path: frames are independent, so a batch is sharded by image
+across ranks (one process per GPU) and the per-rank hit lists are gathered on the host; a single huge frame is
+sharded by pyramid level (every level depends only on the original image, reference channels.py:95-101,125-132).
+There is no data-path collective: the only communication is the host-side gather of the hit records (and the sum of
+the n_loc / n_weak counters), done through `torch.distributed`'s object gather on whatever backend the group has.
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of n_items for `rank` of `world`; sizes differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} of world {world}")
+    base, extra = divmod(int(n_items), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def assign_levels(costs, world):
+    """Greedy longest-processing-time assignment of pyramid levels to ranks.  `costs[l]` ~ work of level l
+    (channel pixels u*v); returns a list of sorted level-index lists, one per rank."""
+    order = sorted(range(len(costs)), key=lambda l: (-costs[l], l))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for l in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(l)
+        load[r] += costs[l]
+    return [sorted(x) for x in out]
+
+
+def normalise_hits(hits):
+    """Order hit records like the reference's output: (frame, level, r, c) ascending (model.py:173-179 per frame)."""
+    if hits.size == 0:
+        return hits
+    order = np.lexsort((hits["c"], hits["r"], hits["level"], hits["frame"]))
+    return hits[order]
+
+
+def gather_hits(local_hits, local_stats, group=None, dst=0):
+    """Host-side gather of per-rank hit records (frame indices already global) and (n_loc, n_weak) counters.
+    Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return normalise_hits(local_hits), tuple(int(x) for x in local_stats)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    payload = (local_hits.tobytes(), local_hits.dtype.descr, tuple(int(x) for x in local_stats))
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object(payload, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None, None
+    parts = [np.frombuffer(b, dtype=np.dtype(d)) for b, d, _ in bucket]
+    hits = np.concatenate(parts) if parts else local_hits
+    stats = (sum(s[0] for *_, s in bucket), sum(s[1] for *_, s in bucket))
+    return normalise_hits(hits), stats
+
+
+def detect_sharded(detect_fn, frames, group=None, dst=0):
+    """Image-sharded detect over the ranks of `group`.
+
+    `frames` is the FULL [B,H,W] batch (every rank holds or can index it); `detect_fn(frames_shard)` runs the local
+    detector and returns (hit records with shard-local `frame` indices, (n_loc, n_weak)) -- on a GPU rank this is
+    `Model.detect_batch(..., return_hits=True)` on that rank's device.  Returns (hits, stats) on `dst`."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    lo, hi = shard_range(len(frames), rank, world)
+    if hi > lo:
+        hits, stats = detect_fn(frames[lo:hi])
+        hits = hits.copy()
+        hits["frame"] += lo
+    else:
+        from ._native import HIT_DTYPE
+        hits, stats = np.empty(0, HIT_DTYPE), (0, 0)
+    return gather_hits(hits, stats, group, dst)

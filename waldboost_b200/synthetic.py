@@ -80,22 +80,32 @@ def channel_quantiles(chns, lo=0.10, hi=0.90):
 
 
 def calibrate_thetas(stage_scores_fn, n_stages, keep_total=1e-4):
-    """"wald" rejection profile: theta_t = the quantile of the running score that keeps a fixed fraction
-    keep_total**(1/T) of the windows entering stage t.  `stage_scores_fn(t, alive_idx)` returns the float32
-    prediction of stage t for the given window indices (any implementation).  Returns float32 thetas."""
-    keep = keep_total ** (1.0 / n_stages)
+    """"wald" rejection profile: theta_t is chosen so that the windows still alive after stage t are (at most) the
+    fraction keep_total**((t+1)/T) of the windows that entered stage 0 -- geometric decay to keep_total, i.e. about
+    1/(1-keep_total**(1/T)) stages evaluated per window.  Ties (flat image regions give many windows the same score)
+    are resolved by rejecting the tied class, never by keeping more than the target; at least one score class is
+    kept.  `stage_scores_fn(t, alive_idx)` returns the float32 prediction of stage t for the given window indices
+    (any implementation).  Returns float32 thetas."""
     thetas = np.empty(n_stages, np.float32)
-    alive, hs = None, None
+    alive, hs, n0 = None, None, 0
     for t in range(n_stages):
         pred = stage_scores_fn(t, alive)
         if hs is None:
             hs = np.zeros(pred.shape, np.float32)
             alive = np.arange(pred.size)
+            n0 = pred.size
         hs = hs + pred.astype(np.float32)
         if hs.size == 0:
             thetas[t] = -np.inf
             continue
-        th = np.float32(np.quantile(hs, 1.0 - keep, method="lower"))
+        target = int(np.floor(n0 * keep_total ** ((t + 1.0) / n_stages)))
+        if hs.size <= target:
+            thetas[t] = -np.inf
+            continue
+        srt = np.sort(hs)[::-1]
+        th = srt[max(target, 1) - 1]                       # keeps >= target windows if there are ties at th
+        if np.count_nonzero(hs >= th) > max(target, 1) and th < srt[0]:
+            th = srt[srt > th].min()                       # reject the tied class instead
         thetas[t] = th
         m = hs >= th
         alive, hs = alive[m], hs[m]
