@@ -86,10 +86,9 @@ def config_B():
     """BASELINE config B / E model: 12x12x4 grad_hist, 1024 depth-2 stages, 'wald' thetas calibrated with the
     reference on a seeded 8 % sample of the windows of all levels of the 1080p frames seed 1000..1003 (SURVEY.md 8d
     calibrates on frame 1000 only; four frames make the thresholds robust to the frames' different noise amplitudes) -> configB_model.pb (used by bench.py), plus the
-    reference's detect() output on a 540x960 crop of that frame (a 1080p reference run costs minutes)."""
+    reference's detect() output on a 540x960 crop of frame 1001 (a 1080p reference run costs minutes)."""
     shape = (12, 12, 4)
     opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=rch.grad_hist)
-    frame = S.synthetic_frame(1000, 1080, 1920)
     lv = []
     for seed in range(1000, 1004):
         lv += [c for c, _ in rch.channel_pyramid(S.synthetic_frame(seed, 1080, 1920), opts) if c.shape[0] > 12 and c.shape[1] > 12]
@@ -100,8 +99,13 @@ def config_B():
     th = calibrate(M, lv, 1024, 1e-4, subsample=0.08, seed=1)
     M.theta = [float(x) for x in th]
     M.save(os.path.join(HERE, "configB_model.pb"))
+    config_B_detect()
+
+
+def config_B_detect():
+    """the reference's detect() with the committed config B model on the centre 540x960 crop of frame 1001."""
     M = RModel.load(os.path.join(HERE, "configB_model.pb"))
-    crop = np.ascontiguousarray(frame[270:810, 480:1440])
+    crop = np.ascontiguousarray(S.synthetic_frame(1001, 1080, 1920)[270:810, 480:1440])
     levels, boxes, scores, n_loc, n_weak = detect_record(M, crop)
     np.savez_compressed(os.path.join(HERE, "configB_detect.npz"), boxes=boxes, scores=scores, n_loc=np.int64(n_loc),
                         n_weak=np.int64(n_weak), level_counts=np.array([r.size for r, *_ in levels]))
@@ -111,6 +115,8 @@ def config_B():
 def main():
     if "--config-b" in sys.argv:
         return config_B()
+    if "--config-b-detect" in sys.argv:
+        return config_B_detect()
     # ---------------------------------------------------------------- small pyramid fixtures
     frame = S.synthetic_frame(1000, 96, 128)
     frame_f = frame.astype(np.float32) + np.random.default_rng(5).random(frame.shape).astype(np.float32)

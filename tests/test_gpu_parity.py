@@ -353,11 +353,11 @@ def test_model_mutation_resyncs_device_copy():
 
 def test_detect_config_B_model_vs_reference_golden():
     """BASELINE config B model (1024 depth-2 stages, wald thetas, the one bench.py times) on a 540x960 crop of frame
-    1000: the reference's own detect() output, bit for bit."""
+    1001: the reference's own detect() output, bit for bit."""
     g = np.load(os.path.join(GOLDEN, "configB_detect.npz"))
     M = wb.Model.load(os.path.join(GOLDEN, "configB_model.pb"))
     assert len(M) == 1024
-    crop = np.ascontiguousarray(S.synthetic_frame(1000, 1080, 1920)[270:810, 480:1440])
+    crop = np.ascontiguousarray(S.synthetic_frame(1001, 1080, 1920)[270:810, 480:1440])
     dt = M.detect(crop)
     assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
     assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])

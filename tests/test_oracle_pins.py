@@ -214,7 +214,7 @@ def test_oracle_config_B_model_equals_reference_golden():
     from waldboost_b200 import synthetic as S
     g = np.load(os.path.join(GOLDEN, "configB_detect.npz"))
     Cs = _load_oracle_model(os.path.join(GOLDEN, "configB_model.pb"))
-    crop = np.ascontiguousarray(S.synthetic_frame(1000, 1080, 1920)[270:810, 480:1440])
+    crop = np.ascontiguousarray(S.synthetic_frame(1001, 1080, 1920)[270:810, 480:1440])
     boxes, scores, _ = Cs.detect(crop)
     assert np.array_equal(boxes, g["boxes"]) and np.array_equal(scores, g["scores"])
     assert (Cs.n_loc, Cs.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
