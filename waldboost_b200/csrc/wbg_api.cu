@@ -337,9 +337,10 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
                 if (Lf[ll] < 0 && Lf[lr] < 0 && Lf[rl] < 0 && Lf[rr] < 0) {
                     StageD2& s = d2[t];
                     const NodeDev* nd = &nodes[(size_t)t * N];
-                    s.off0 = nd[0].off; s.thr0 = nd[0].thr;
-                    s.off1 = nd[a].off; s.thr1 = nd[a].thr;
-                    s.off4 = nd[b].off; s.thr4 = nd[b].thr;
+                    // byte offsets inside the planar shared-memory patch
+                    s.off0 = 4 * nd[0].off; s.thr0 = nd[0].thr;
+                    s.off1 = 4 * nd[a].off; s.thr1 = nd[a].thr;
+                    s.off4 = 4 * nd[b].off; s.thr4 = nd[b].thr;
                     s.p2 = nd[ll].pred; s.p3 = nd[lr].pred; s.p5 = nd[rl].pred; s.p6 = nd[rr].pred;
                     s.theta = d->theta[t]; s.pad_ = 0.f;
                     is_d2 = true;

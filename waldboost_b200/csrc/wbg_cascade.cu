@@ -60,6 +60,85 @@ __device__ __forceinline__ int find_level_by_ctile(const LevelDev* levels, int n
     return lo;
 }
 
+// Shared-memory word at a 32-bit shared-window byte address.  Not volatile on purpose: the patch is read-only once
+// staged, so the compiler may hoist these loads across stages of an unrolled round (software pipelining).
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// One round (stages [t, t_end)) of the cascade for the first NK window slots of a thread; wa[k] is the shared-memory
+// byte address of the window's origin inside the staged patch.
+//
+// Depth-2 stages: the 48-byte stage record (byte offsets pre-scaled) is read once per stage and shared by the NK
+// slots; both children are gathered speculatively, so the three shared-memory loads of a slot are independent of
+// each other and of the previous stage -- only the float32 accumulation and the theta test form a dependency chain.
+// Dead slots keep executing with their results ignored (their lanes are idle anyway while the warp is live).
+// `last[k]` is the index after the last stage the slot entered alive (n_weak bookkeeping, model.py:252).
+// Generic topology: follow the left/right links of the node records (training.py:88-95).
+template <bool D2, int NK>
+__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[CAS_WPT], float (&hs)[CAS_WPT], bool (&alive)[CAS_WPT],
+                                          int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
+                                          const float* __restrict__ thetas) {
+    if (D2) {
+        int last[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) last[k] = t;
+#pragma unroll 4
+        for (int s = t; s < t_end; ++s) {
+            const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
+            const int4 A = rec[0], B = rec[1], Cc = rec[2];
+            const float thr0 = __int_as_float(A.y), thr1 = __int_as_float(A.w), thr4 = __int_as_float(B.y);
+            const float p2 = __int_as_float(B.z), p3 = __int_as_float(B.w);
+            const float p5 = __int_as_float(Cc.x), p6 = __int_as_float(Cc.y), theta = __int_as_float(Cc.z);
+            const int s1 = s + 1;
+            float x0[NK], xa[NK], xb[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                x0[k] = lds_f32(wa[k] + (unsigned)A.x);
+                xa[k] = lds_f32(wa[k] + (unsigned)A.z);
+                xb[k] = lds_f32(wa[k] + (unsigned)B.x);
+            }
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const float pa = (xa[k] <= thr1) ? p2 : p3;    // training.py:92 -- left iff X <= threshold
+                const float pb = (xb[k] <= thr4) ? p5 : p6;
+                hs[k] += (x0[k] <= thr0) ? pa : pb;            // float32 accumulation in stage order (model.py:251)
+                last[k] = alive[k] ? s1 : last[k];
+            }
+            if (theta != -CUDART_INF_F) {                      // model.py:253 -- theta == -inf: no test at this stage
+#pragma unroll
+                for (int k = 0; k < NK; ++k) alive[k] = alive[k] && hs[k] >= theta;   // model.py:255-258
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) my_weak += (unsigned)(last[k] - t);
+    } else {
+        const float* tile = nullptr;
+        asm("cvta.shared.u64 %0, %1;" : "=l"(tile) : "l"((unsigned long long)tile_base));
+        for (int s = t; s < t_end; ++s) {
+            const NodeDev* __restrict__ nb = nodes + (size_t)s * N;
+            const float theta = __ldg(thetas + s);
+            const bool test = theta != -CUDART_INF_F;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                if (alive[k]) {
+                    const float* w = tile + ((wa[k] - tile_base) >> 2);
+                    NodeDev nd = load_node(nb);
+                    while (nd.left >= 0) {
+                        const float x = w[nd.off];
+                        nd = load_node(nb + ((x <= nd.thr) ? nd.left : nd.right));
+                    }
+                    hs[k] += nd.pred;
+                    ++my_weak;
+                    alive[k] = !test || hs[k] >= theta;
+                }
+            }
+        }
+    }
+}
+
 template <bool D2>
 __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -67,7 +146,7 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
     float* s_score = tile + ((p.C * p.plane + 3) & ~3);
     unsigned short* s_woff = reinterpret_cast<unsigned short*>(s_score + CAS_MAX_WIN);
     __shared__ int s_tot[CAS_WPT * (CAS_THREADS / 32)];
-    __shared__ int s_nact;
+    __shared__ int s_cnt[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x / p.tiles_per_frame;
@@ -82,6 +161,7 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
     const int rows_valid = min(p.TR, win_rows - r0), cols_valid = min(p.TC, win_cols - c0);
     const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;
     const int pitch = p.pitch, plane = p.plane;
+    if (tid < 3) s_cnt[tid] = 0;
 
     // ---- stage the channel patch, HWC in HBM -> planar in shared memory
     const float* __restrict__ src = p.chns + (long long)frame * p.chn_stride + chn_off + ((long long)r0 * v + c0) * p.C;
@@ -100,79 +180,58 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
             for (int ch = 0; ch < p.C; ++ch) d[ch * plane] = __ldg(s + ch);
         }
     }
-    // ---- all windows of the tile start alive with score 0 (model.py:243-247), row-major
+    // ---- every window of the tile starts alive with score 0 (model.py:243-247).  Slot idx = tid + k*CAS_THREADS
+    // holds window idx of the tile in row-major order, so a warp's lanes gather adjacent shared-memory words.
     const int nwin = rows_valid * cols_valid;
-    for (int i = tid; i < nwin; i += CAS_THREADS) {
-        const int lr = i / cols_valid, lc = i - lr * cols_valid;
-        s_woff[i] = (unsigned short)(lr * pitch + lc);
-        s_score[i] = 0.f;
-    }
     __syncthreads();
+    unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
+    asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
+    unsigned wa[CAS_WPT];
+    float hs[CAS_WPT];
+    bool alive[CAS_WPT];
+#pragma unroll
+    for (int k = 0; k < CAS_WPT; ++k) {
+        const int idx = tid + k * CAS_THREADS;
+        alive[k] = idx < nwin;
+        const int lr = alive[k] ? idx / cols_valid : 0, lc = alive[k] ? idx - lr * cols_valid : 0;
+        wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
+        hs[k] = 0.f;
+    }
 
-    int n_act = nwin, t = 0;
+    int n_slots = nwin, n_alive = nwin, t = 0, round = 0;
     unsigned my_weak = 0;
-    while (t < p.T && n_act > 0) {
-        // stage blocks 1,1,2,4,8,16 then 32 stages: real cascades reject most windows in the first stages
-        const int t_end = min(p.T, t < 1 ? 1 : (t < 32 ? 2 * t : t + 32));
-        int woff[CAS_WPT];
-        float hs[CAS_WPT];
-        bool alive[CAS_WPT];
+    while (t < p.T && n_alive > 0) {
+        // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
+        const int t_end = min(p.T, t + (n_slots > CAS_THREADS ? 8 : (n_slots > 64 ? 16 : 32)));
+        bool mine = false;
+#pragma unroll
+        for (int k = 0; k < CAS_WPT; ++k) mine |= alive[k];
+        if (__any_sync(0xffffffffu, mine)) {
+            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*CAS_THREADS < n_slots (warp-uniform)
+            const int first = warp << 5;
+            if (first + 2 * CAS_THREADS < n_slots) run_round<D2, 4>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + CAS_THREADS < n_slots) run_round<D2, 2>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else run_round<D2, 1>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+        }
+        // ---- how many windows of the tile are still alive
+        unsigned bal[CAS_WPT];
+        int wcnt = 0;
 #pragma unroll
         for (int k = 0; k < CAS_WPT; ++k) {
-            const int idx = tid + k * CAS_THREADS;
-            alive[k] = idx < n_act;
-            woff[k] = alive[k] ? s_woff[idx] : 0;
-            hs[k] = alive[k] ? s_score[idx] : 0.f;
+            bal[k] = __ballot_sync(0xffffffffu, alive[k]);
+            wcnt += __popc(bal[k]);
         }
-        for (int s = t; s < t_end; ++s) {
-            bool any = false;
-            if (D2) {
-                const StageD2& S = c_d2[s];
-                const float theta = S.theta;
-                const bool test = theta != -CUDART_INF_F;
-#pragma unroll
-                for (int k = 0; k < CAS_WPT; ++k) {
-                    if (alive[k]) {
-                        const float x0 = tile[woff[k] + S.off0];
-                        const bool l0 = x0 <= S.thr0;               // training.py:92 -- left iff X <= threshold
-                        const int off = l0 ? S.off1 : S.off4;
-                        const float thr = l0 ? S.thr1 : S.thr4;
-                        const float x1 = tile[woff[k] + off];
-                        const bool l1 = x1 <= thr;
-                        const float pa = l1 ? S.p2 : S.p3;
-                        const float pb = l1 ? S.p5 : S.p6;
-                        hs[k] += l0 ? pa : pb;                        // float32 accumulation in stage order
-                        ++my_weak;
-                        if (test && !(hs[k] >= theta)) alive[k] = false;   // model.py:253-258
-                        any |= alive[k];
-                    }
-                }
-            } else {
-                const NodeDev* __restrict__ nb = p.nodes + (size_t)s * p.N;
-                const float theta = __ldg(p.theta + s);
-                const bool test = theta != -CUDART_INF_F;
-#pragma unroll
-                for (int k = 0; k < CAS_WPT; ++k) {
-                    if (alive[k]) {
-                        NodeDev nd = load_node(nb);
-                        while (nd.left >= 0) {
-                            const float x = tile[woff[k] + nd.off];
-                            const int nxt = (x <= nd.thr) ? nd.left : nd.right;
-                            nd = load_node(nb + nxt);
-                        }
-                        hs[k] += nd.pred;
-                        ++my_weak;
-                        if (test && !(hs[k] >= theta)) alive[k] = false;
-                        any |= alive[k];
-                    }
-                }
-            }
-            if (!__any_sync(0xffffffffu, any)) break;
-        }
-        // ---- order-preserving re-pack of the CTA's survivors
-        unsigned bal[CAS_WPT];
-#pragma unroll
-        for (int k = 0; k < CAS_WPT; ++k) bal[k] = __ballot_sync(0xffffffffu, alive[k]);
+        const int par = round % 3;
+        if (lane == 0 && wcnt) atomicAdd(&s_cnt[par], wcnt);
+        if (tid == 0) s_cnt[(round + 1) % 3] = 0;
+        __syncthreads();
+        n_alive = s_cnt[par];
+        t = t_end;
+        ++round;
+        if (n_alive == 0 || t >= p.T) break;
+        if (n_alive * 3 > n_slots || n_slots <= 32) continue;
+
+        // ---- order-preserving re-pack of the CTA's survivors into the first n_alive slots
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < CAS_WPT; ++k) s_tot[k * (CAS_THREADS / 32) + warp] = __popc(bal[k]);
@@ -187,29 +246,37 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
                 if (lane >= d) inc += o;
             }
             s_tot[lane] = inc - val;
-            if (lane == 31) s_nact = inc;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < CAS_WPT; ++k) {
             if (alive[k]) {
                 const int pos = s_tot[k * (CAS_THREADS / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
-                s_woff[pos] = (unsigned short)woff[k];
+                s_woff[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
                 s_score[pos] = hs[k];
             }
         }
-        n_act = s_nact;
         __syncthreads();
-        t = t_end;
+        n_slots = n_alive;
+#pragma unroll
+        for (int k = 0; k < CAS_WPT; ++k) {
+            const int idx = tid + k * CAS_THREADS;
+            alive[k] = idx < n_slots;
+            wa[k] = tile_base + 4u * (alive[k] ? (unsigned)s_woff[idx] : 0u);
+            hs[k] = alive[k] ? s_score[idx] : 0.f;
+        }
     }
 
     // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
-    for (int i = tid; i < n_act; i += CAS_THREADS) {
-        const int wo = s_woff[i];
-        const int lr = wo / pitch, lc = wo - lr * pitch;
-        const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
-        p.score[(long long)frame * p.score_stride + widx] = s_score[i];
-        atomicOr(p.mask + (long long)frame * p.mask_stride + (widx >> 5), 1u << (unsigned)(widx & 31));
+#pragma unroll
+    for (int k = 0; k < CAS_WPT; ++k) {
+        if (alive[k]) {
+            const int wo = (int)((wa[k] - tile_base) >> 2);
+            const int lr = wo / pitch, lc = wo - lr * pitch;
+            const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
+            p.score[(long long)frame * p.score_stride + widx] = hs[k];
+            atomicOr(p.mask + (long long)frame * p.mask_stride + (widx >> 5), 1u << (unsigned)(widx & 31));
+        }
     }
     // ---- stats (model.py:248,252): n_loc += windows, n_weak += windows entering each stage
     unsigned w = my_weak;
