@@ -226,9 +226,9 @@ def run_gpu(args):
                "sample": f"{cores} frames of 1920x1080 (one per worker process), oracle/wb_oracle.py Cascade.detect, "
                          f"eval_cost {n_weak_c / max(n_loc_c, 1):.1f}, {busy:.1f} s"}
 
-    from __graft_entry__ import build
+    from waldboost_b200.build import build
     if local == 0:
-        build()
+        build()            # in-tree nvcc build of libwbg.so if the sources changed (normally a no-op)
     barrier()
     import waldboost_b200 as wb
     from waldboost_b200 import synthetic as S

@@ -103,7 +103,7 @@ struct PyrParams {
     int n_levels, tiles_per_frame;
     float* chns;
     long long chn_stride;
-    int C, S, smooth, kind, n_bins, full, G;
+    int C, S, smooth, kind, n_bins, full, G, fast4;
     float bias, eps;
     float tri[2 * WBG_MAX_NORM + 1];
     double cs[WBG_MAX_BINS], sn[WBG_MAX_BINS];
@@ -326,6 +326,236 @@ __global__ void __launch_bounds__(PYR_THREADS) level_kernel(const PyrParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ grad_hist fast kernel
+// Same arithmetic as level_kernel for the grad_hist channel function (channels.py:40-52), restructured so that every
+// tile dimension is a compile-time constant and no value is computed twice:
+//   P0  bilinear taps of the tile's rows / columns (float64, scipy op order) + a float32 copy of the weights
+//   P1  resized tile.  uint8 images: a float32 interpolation decides the truncated value whenever it is provably
+//       not within DELTA of an integer (its error is < 1e-4); otherwise -- and always for float32 images -- the
+//       float64 expression of scipy's zoom is evaluated, so the result is the reference's bit for bit.
+//   P2  one thread per pooled pixel: the (S+2)^2 resized neighbourhood is read once into registers, the SxS
+//       gradients are built from shared partial sums (exact in float32 for integer-valued images), projected on the
+//       orientation bins in float64 like NumPy does, pooled in float32 in the reference's add order and stored as
+//       float64 for the smoothing pass.
+//   P3  3x3 smoothing accumulated in float64 (Numba typing), zero border ring, float4 HWC store.
+struct TapF {
+    int i0, i1;
+    float w1f, pad_;
+    double w0, w1;
+};
+
+constexpr float RESAMPLE_DELTA = 1e-3f;
+
+template <typename T, int S, int SM>
+__global__ void __launch_bounds__(PYR_THREADS) level_hist_kernel(const PyrParams p) {
+    constexpr int TU = PYR_TU, TV = PYR_TV;
+    constexpr int PH = TU + 2 * SM, PW = TV + 2 * SM;     // pooled tile incl. the smoothing halo
+    constexpr int FH = S * PH, FW = S * PW;               // full-resolution channel pixels
+    constexpr int RH = FH + 2, RW = FW + 2;               // resized pixels incl. the gradient halo
+    constexpr int RWP = (RW + 1) & ~1;                    // even pitch: 8-byte aligned row pairs
+    constexpr int NB = S + 2;                             // neighbourhood edge per pooled pixel
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    int lo = 0, hi = p.n_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.levels[mid].ptile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const LevelDev* __restrict__ L = p.levels + lo;
+    const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
+    const int local = tile_id - L->ptile0;
+    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ou0 = ty * TU, ov0 = tx * TV;
+    const int C = p.C;
+    const int ry0 = S * (ou0 - SM) - 1, rx0 = S * (ov0 - SM) - 1;
+
+    TapF* s_tapr = reinterpret_cast<TapF*>(smem_raw);
+    TapF* s_tapc = s_tapr + RH;
+    float* s_R = reinterpret_cast<float*>(s_tapc + RW);                       // [RH][RWP]
+    double* s_P = reinterpret_cast<double*>(s_R + RH * RWP);                  // [C][PH*PW]
+
+    const T* __restrict__ src = (L->oct == 0)
+        ? reinterpret_cast<const T*>(p.img) + (long long)frame * p.img_stride
+        : reinterpret_cast<const T*>(p.oct_ws) + (long long)frame * p.oct_stride + L->src_off;
+    const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
+    const bool identity = L->identity != 0;
+
+    // ---- P0: taps
+    if (!identity) {
+        const double zr = L->zoom_r, zc = L->zoom_c;
+        for (int i = tid; i < RH + RW; i += PYR_THREADS) {
+            const bool row = i < RH;
+            const Tap t = row ? make_tap(reflect_idx(ry0 + i, nh), zr, sh) : make_tap(reflect_idx(rx0 + (i - RH), nw), zc, sw);
+            TapF f;
+            f.i0 = t.i0; f.i1 = t.i1; f.w1f = (float)t.w1; f.pad_ = 0.f; f.w0 = t.w0; f.w1 = t.w1;
+            if (row) s_tapr[i] = f; else s_tapc[i - RH] = f;
+        }
+        __syncthreads();
+    }
+    // ---- P1: resized tile, cast back to the input dtype (channels.py:132), kept as float32
+    for (int i = tid; i < RH * RW; i += PYR_THREADS) {
+        const int iy = i / RW, ix = i - iy * RW;
+        float val;
+        if (identity) {
+            val = (float)src[(long long)reflect_idx(ry0 + iy, nh) * sw + reflect_idx(rx0 + ix, nw)];
+        } else {
+            const TapF* a = s_tapr + iy;
+            const TapF* b = s_tapc + ix;
+            const int ai0 = a->i0, ai1 = a->i1, bi0 = b->i0, bi1 = b->i1;
+            const T* r0p = src + (long long)ai0 * sw;
+            const T* r1p = src + (long long)ai1 * sw;
+            const T q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
+            bool exact = true;
+            val = 0.f;
+            if (sizeof(T) == 1) {
+                const float f00 = (float)q00, f01 = (float)q01, f10 = (float)q10, f11 = (float)q11;
+                const float wx = b->w1f, wy = a->w1f;
+                const float top = fmaf(wx, f01 - f00, f00), bot = fmaf(wx, f11 - f10, f10);
+                const float r = fmaf(wy, bot - top, top);
+                const float tr = truncf(r), fr = r - tr;
+                val = tr;
+                // the float32 estimate is within 1e-4 of scipy's float64 sum: away from an integer it truncates alike
+                exact = !(fr > RESAMPLE_DELTA && fr < 1.f - RESAMPLE_DELTA) && ((int)q00 | (int)q01 | (int)q10 | (int)q11) != 0;
+            }
+            if (exact) {
+                const double w0r = a->w0, w1r = a->w1, w0c = b->w0, w1c = b->w1;
+                double t = __dmul_rn(__dmul_rn((double)q00, w0r), w0c);
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, w0r), w1c));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, w1r), w0c));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, w1r), w1c));
+                val = finish_resample<T>(t, mm.x, mm.y);
+            }
+        }
+        s_R[iy * RWP + ix] = val;
+    }
+    __syncthreads();
+
+    // ---- P2: gradients -> orientation bins -> SxS mean, one pooled pixel per thread
+    const bool fast4 = p.fast4 != 0 && sizeof(T) == 1;
+    for (int i = tid; i < PH * PW; i += PYR_THREADS) {
+        const int py = i / PW, px = i - py * PW;
+        const int pu = ou0 - SM + py, pv = ov0 - SM + px;
+        if (pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
+        float R[NB][NB];
+        const float* rp = s_R + (S * py) * RWP + S * px;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+            if (S == 2) {
+                const float2 x0 = *reinterpret_cast<const float2*>(rp + a * RWP);
+                const float2 x1 = *reinterpret_cast<const float2*>(rp + a * RWP + 2);
+                R[a][0] = x0.x; R[a][1] = x0.y; R[a][2] = x1.x; R[a][3] = x1.y;
+            } else {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) R[a][b] = rp[a * RWP + b];
+            }
+        }
+        // channels.py:16-21: each 1-D pass accumulates in float64 and stores float32.  For uint8 images every value
+        // is a small integer and the float32 expression is exact; float32 images take the float64 expression.
+        auto smooth121 = [](float prev, float mid, float next) -> float {
+            if (sizeof(T) == 1) return fmaf(2.f, mid, prev + next);
+            return (float)(2.0 * (double)mid + ((double)prev + (double)next));
+        };
+        float gx[S][S], gy[S][S];
+#pragma unroll
+        for (int a = 0; a < S; ++a) {
+            float V[NB];       // [1,2,1] along rows at row a+1
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                V[b] = smooth121(R[a][b], R[a + 1][b], R[a + 2][b]);
+#pragma unroll
+            for (int b = 0; b < S; ++b) gx[a][b] = __fsub_rn(V[b], V[b + 2]);
+        }
+#pragma unroll
+        for (int b = 0; b < S; ++b) {
+            float Hh[NB];      // [1,2,1] along columns at column b+1
+#pragma unroll
+            for (int a = 0; a < NB; ++a)
+                Hh[a] = smooth121(R[a][b], R[a][b + 1], R[a][b + 2]);
+#pragma unroll
+            for (int a = 0; a < S; ++a) gy[a][b] = __fsub_rn(Hh[a], Hh[a + 2]);
+        }
+        double* dst = s_P + i;
+        for (int bin = 0; bin < p.n_bins; ++bin) {
+            const double cb = p.cs[bin], sb = p.sn[bin];
+            float acc = 0.f;
+#pragma unroll
+            for (int sub = 0; sub < S * S; ++sub) {
+                // order of channels.py:61-64: a00, a10 (next row), a01 (next column), a11
+                const int dy = sub & (S - 1), dx = sub >> (S - 1);
+                const float gxf = gx[dy][dx], gyf = gy[dy][dx];
+                float ch;
+                if (fast4 && bin == 0) ch = gxf;                        // gx*1.0 - gy*0.0
+                else if (fast4 && bin == 2 && gyf != 0.f) ch = -gyf;    // gx*6.1e-17 - gy*1.0 rounds to -gy (|gy| >= 1)
+                else ch = (float)__dadd_rn(__dmul_rn((double)gxf, cb), -__dmul_rn((double)gyf, sb));   // channels.py:50 (NumPy 2)
+                float val = fmaxf(__fsub_rn(fabsf(ch), p.bias), 0.f);
+                if (p.full) val = __fmul_rn((float)((ch > 0.f) - (ch < 0.f)), val);
+                acc = sub == 0 ? val : __fadd_rn(acc, val);
+            }
+            dst[bin * (PH * PW)] = (double)(S == 2 ? __fmul_rn(acc, 0.25f) : acc);
+        }
+    }
+    __syncthreads();
+
+    // ---- P3: 3x3 smoothing with a zero border ring (channels.py:78-90), HWC store
+    float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
+    for (int pix = tid; pix < TU * TV; pix += PYR_THREADS) {
+        const int oy = pix / TV, ox = pix - oy * TV;
+        const int ou = ou0 + oy, ov = ov0 + ox;
+        if (ou >= u || ov >= v) continue;
+        const bool ring = SM && (ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1);
+        float* o = out + ((long long)ou * v + ov) * C;
+        const double* q0 = s_P + (oy + SM) * PW + (ox + SM);
+        float r4[4];
+        for (int c = 0; c < C; ++c) {
+            const double* q = q0 + c * (PH * PW);
+            float r;
+            if (!SM) {
+                r = (float)q[0];
+            } else if (ring) {
+                r = 0.f;
+            } else {
+                double a = q[-PW - 1] + 2.0 * q[-PW];
+                a += q[-PW + 1];
+                a += 2.0 * q[-1];
+                a += 4.0 * q[0];
+                a += 2.0 * q[1];
+                a += q[PW - 1];
+                a += 2.0 * q[PW];
+                a += q[PW + 1];
+                r = (float)(a * 0.0625);
+            }
+            if (C == 4) r4[c] = r; else o[c] = r;
+        }
+        if (C == 4) *reinterpret_cast<float4*>(o) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+    }
+}
+
+template <int S, int SM>
+static constexpr size_t hist_smem_bytes(int C) {
+    constexpr int PH = PYR_TU + 2 * SM, PW = PYR_TV + 2 * SM, RH = S * PH + 2, RW = S * PW + 2, RWP = (RW + 1) & ~1;
+    return (size_t)(RH + RW) * sizeof(TapF) + (size_t)RH * RWP * 4 + (size_t)C * PH * PW * 8 + 16;
+}
+
+template <typename T>
+static int launch_hist_level(const PyrParams& p, int S, int SM, long long grid, cudaStream_t stream) {
+#define WBG_HIST_CASE(SS, MM)                                                                                        \
+    if (S == SS && SM == MM) {                                                                                       \
+        const size_t smem = hist_smem_bytes<SS, MM>(p.C);                                                            \
+        WBG_CUDA_TRY(cudaFuncSetAttribute(level_hist_kernel<T, SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);                                                               \
+        level_hist_kernel<T, SS, MM><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);                              \
+        wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);                                                                 \
+        WBG_CUDA_TRY(cudaGetLastError());                                                                            \
+        return WBG_OK;                                                                                               \
+    }
+    WBG_HIST_CASE(2, 1) WBG_HIST_CASE(2, 0) WBG_HIST_CASE(1, 1) WBG_HIST_CASE(1, 0)
+#undef WBG_HIST_CASE
+    wbg_set_error("channel pyramid: unsupported shrink %d", S);
+    return WBG_EINVAL;
+}
+
 static size_t level_smem_bytes(const wbg_channel_opts& o, int C) {
     const int S = o.shrink, hsm = o.smooth == 1 ? 1 : 0;
     const bool has_mag = o.kind != WBG_CH_GRAD_HIST;
@@ -385,6 +615,14 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
     }
     for (int b = 0; b < WBG_MAX_BINS; ++b) { p.cs[b] = o.cos_t[b]; p.sn[b] = o.sin_t[b]; }
 
+    const long long grid_h = (long long)plan->ptiles * batch;
+    WBG_REQUIRE(grid_h <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid_h);
+    if (o.kind == WBG_CH_GRAD_HIST) {
+        // the orientation table of the default 4-bin histogram: cos/sin = (1,0), (c,s), (6.1e-17,1), (-s,c)
+        p.fast4 = (o.n_bins == 4 && !o.full && o.cos_t[0] == 1.0 && o.sin_t[0] == 0.0 && o.sin_t[2] == 1.0 &&
+                   o.cos_t[2] > -1e-15 && o.cos_t[2] < 1e-15) ? 1 : 0;
+        return launch_hist_level<T>(p, o.shrink, o.smooth == 1 ? 1 : 0, grid_h, stream);
+    }
     const size_t smem = level_smem_bytes(o, plan->C);
     WBG_REQUIRE(smem <= 220 * 1024, "channel pyramid: tile needs %zu bytes of shared memory", smem);
     WBG_CUDA_TRY(cudaFuncSetAttribute(level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
