@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -75,31 +76,39 @@ extern "C" int wbg_profile_read(double* ms, int64_t* launches) {
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
-    // Largest tile whose planar channel patch + window lists fit a budget that keeps >= 2 CTAs per SM.
-    const int budget = 100 * 1024;
-    const int cand[][2] = {{16, 64}, {16, 32}, {8, 32}, {8, 16}, {4, 16}, {2, 16}, {1, 16}};
+    // Tile candidates, largest first.  A big tile keeps the lanes of the sparse late stages fuller (the survivors of
+    // 4096 windows share a CTA) and halves the halo overhead; it must leave room for two CTAs per SM.
+    struct Cand { int TR, TC, threads, wpt, budget; };
+    const Cand cand[] = {{32, 128, 512, 8, 112 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
+                         {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
+                         {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
+    const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
+    int idx = 0;
     for (auto& c : cand) {
-        int TR = c[0], TC = c[1];
-        int rows = TR + m - 1;
-        int pitch = TC + n - 1;
-        pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are compacted
-        long long plane = (long long)rows * pitch;
-        long long bytes = plane * C * 4 + (long long)CAS_MAX_WIN * (4 + 4) + 256;
-        if (bytes <= budget) {
-            g->TR = TR; g->TC = TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
-            g->smem_bytes = (int)bytes;
+        if (idx++ < skip) continue;
+        const int rows = c.TR + m - 1;
+        int pitch = c.TC + n - 1;
+        pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are re-packed
+        const long long plane = (long long)rows * pitch;
+        const int list_cap = c.threads * c.wpt / 2;
+        const long long bytes = plane * C * 4 + (long long)list_cap * (4 + 2) + 256;
+        if (bytes <= c.budget && plane < 65536) {
+            g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
+            g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap;
+            g->compact_num = env_int("WBG_CAS_COMPACT_NUM", 1);
+            g->compact_den = env_int("WBG_CAS_COMPACT_DEN", 2);
+            if (g->compact_num < 1 || g->compact_den < 2 * g->compact_num) { g->compact_num = 1; g->compact_den = 2; }
+            g->round_full = env_int("WBG_CAS_ROUND_FULL", 16);
+            g->round_mid = env_int("WBG_CAS_ROUND_MID", 32);
+            g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 64);
             return true;
         }
-    }
-    // last resort: one CTA per SM with the smallest tile
-    int TR = 1, TC = 16, rows = m, pitch = TC + n - 1;
-    pitch += (pitch % 2 == 0);
-    long long plane = (long long)rows * pitch;
-    long long bytes = plane * C * 4 + (long long)CAS_MAX_WIN * 8 + 256;
-    if (bytes <= 220 * 1024) {
-        g->TR = TR; g->TC = TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane; g->smem_bytes = (int)bytes;
-        return true;
     }
     return false;
 }

@@ -18,6 +18,7 @@
 // No tensor cores: nothing here is a contraction.  The stage loop is bound by shared-memory gathers and issue
 // slots; HBM traffic is one read of the channel pyramid.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "wbg_internal.h"
 
@@ -33,6 +34,7 @@ struct CascadeParams {
     int N, T;
     int C, m, n;
     int TR, TC, pitch, plane;
+    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail, flags;
     unsigned* mask;
     long long mask_stride;  // words per frame
     float* score;
@@ -71,21 +73,21 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
 // One round (stages [t, t_end)) of the cascade for the first NK window slots of a thread; wa[k] is the shared-memory
 // byte address of the window's origin inside the staged patch.
 //
-// Depth-2 stages: the 48-byte stage record (byte offsets pre-scaled) is read once per stage and shared by the NK
-// slots; both children are gathered speculatively, so the three shared-memory loads of a slot are independent of
-// each other and of the previous stage -- only the float32 accumulation and the theta test form a dependency chain.
-// Dead slots keep executing with their results ignored (their lanes are idle anyway while the warp is live).
-// `last[k]` is the index after the last stage the slot entered alive (n_weak bookkeeping, model.py:252).
+// Depth-2 stages: the 48-byte stage record (byte offsets pre-scaled) is read once per stage through the uniform
+// datapath and shared by the NK slots; both children are gathered speculatively, so the three shared-memory loads of
+// a slot are independent of each other and of the previous stage -- only the float32 accumulation and the theta test
+// form a dependency chain.  Dead slots keep executing with their results ignored (their lanes are idle anyway while
+// the warp is live).  `last[k]` is the index after the last stage the slot entered alive (n_weak, model.py:252).
 // Generic topology: follow the left/right links of the node records (training.py:88-95).
-template <bool D2, int NK>
-__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[CAS_WPT], float (&hs)[CAS_WPT], bool (&alive)[CAS_WPT],
+template <bool D2, int NK, int WPT>
+__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], bool (&alive)[WPT],
                                           int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
                                           const float* __restrict__ thetas) {
     if (D2) {
         int last[NK];
 #pragma unroll
         for (int k = 0; k < NK; ++k) last[k] = t;
-#pragma unroll 4
+#pragma unroll 2
         for (int s = t; s < t_end; ++s) {
             const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
             const int4 A = rec[0], B = rec[1], Cc = rec[2];
@@ -93,19 +95,23 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             const float p2 = __int_as_float(B.z), p3 = __int_as_float(B.w);
             const float p5 = __int_as_float(Cc.x), p6 = __int_as_float(Cc.y), theta = __int_as_float(Cc.z);
             const int s1 = s + 1;
-            float x0[NK], xa[NK], xb[NK];
+            constexpr int G = NK < 4 ? NK : 4;               // slots in flight together (bounds live registers)
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                x0[k] = lds_f32(wa[k] + (unsigned)A.x);
-                xa[k] = lds_f32(wa[k] + (unsigned)A.z);
-                xb[k] = lds_f32(wa[k] + (unsigned)B.x);
-            }
+            for (int g = 0; g < NK; g += G) {
+                float x0[G], xa[G], xb[G];
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const float pa = (xa[k] <= thr1) ? p2 : p3;    // training.py:92 -- left iff X <= threshold
-                const float pb = (xb[k] <= thr4) ? p5 : p6;
-                hs[k] += (x0[k] <= thr0) ? pa : pb;            // float32 accumulation in stage order (model.py:251)
-                last[k] = alive[k] ? s1 : last[k];
+                for (int k = 0; k < G; ++k) {
+                    x0[k] = lds_f32(wa[g + k] + (unsigned)A.x);
+                    xa[k] = lds_f32(wa[g + k] + (unsigned)A.z);
+                    xb[k] = lds_f32(wa[g + k] + (unsigned)B.x);
+                }
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const float pa = (xa[k] <= thr1) ? p2 : p3;    // training.py:92 -- left iff X <= threshold
+                    const float pb = (xb[k] <= thr4) ? p5 : p6;
+                    hs[g + k] += (x0[k] <= thr0) ? pa : pb;        // float32 accumulation in stage order (model.py:251)
+                    last[g + k] = alive[g + k] ? s1 : last[g + k];
+                }
             }
             if (theta != -CUDART_INF_F) {                      // model.py:253 -- theta == -inf: no test at this stage
 #pragma unroll
@@ -139,13 +145,17 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
     }
 }
 
-template <bool D2>
-__global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParams p) {
+template <bool D2, int THREADS, int WPT>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kernel(const CascadeParams p) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int ENTRIES = WPT * WARPS;          // (slot, warp) ballot counts, a multiple of 32
+    constexpr int EPL = ENTRIES / 32;             // entries scanned per lane of warp 0
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     float* s_score = tile + ((p.C * p.plane + 3) & ~3);
-    unsigned short* s_woff = reinterpret_cast<unsigned short*>(s_score + CAS_MAX_WIN);
-    __shared__ int s_tot[CAS_WPT * (CAS_THREADS / 32)];
+    unsigned short* s_woff = reinterpret_cast<unsigned short*>(s_score + p.list_cap);
+    __shared__ int s_tot[ENTRIES];                // survivors per (slot, warp); stays 0 for retired warps
+    __shared__ int s_pre[ENTRIES];                // exclusive prefix of s_tot in slot-major order
     __shared__ int s_cnt[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,58 +176,61 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
     // ---- stage the channel patch, HWC in HBM -> planar in shared memory
     const float* __restrict__ src = p.chns + (long long)frame * p.chn_stride + chn_off + ((long long)r0 * v + c0) * p.C;
     if (p.C == 4) {
-        for (int i = tid; i < lrows * lcols; i += CAS_THREADS) {
+        for (int i = tid; i < lrows * lcols; i += THREADS) {
             const int rr = i / lcols, cc = i - rr * lcols;
             const float4 x = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * v + cc) * 4));
             float* d = tile + rr * pitch + cc;
             d[0] = x.x; d[plane] = x.y; d[2 * plane] = x.z; d[3 * plane] = x.w;
         }
     } else {
-        for (int i = tid; i < lrows * lcols; i += CAS_THREADS) {
+        for (int i = tid; i < lrows * lcols; i += THREADS) {
             const int rr = i / lcols, cc = i - rr * lcols;
             const float* s = src + ((long long)rr * v + cc) * p.C;
             float* d = tile + rr * pitch + cc;
             for (int ch = 0; ch < p.C; ++ch) d[ch * plane] = __ldg(s + ch);
         }
     }
-    // ---- every window of the tile starts alive with score 0 (model.py:243-247).  Slot idx = tid + k*CAS_THREADS
-    // holds window idx of the tile in row-major order, so a warp's lanes gather adjacent shared-memory words.
+    // ---- every window of the tile starts alive with score 0 (model.py:243-247).  Slot idx = tid + k*THREADS holds
+    // window idx of the tile in row-major order, so a warp's lanes gather adjacent shared-memory words.
     const int nwin = rows_valid * cols_valid;
     __syncthreads();
     unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
     asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
-    unsigned wa[CAS_WPT];
-    float hs[CAS_WPT];
-    bool alive[CAS_WPT];
+    unsigned wa[WPT];
+    float hs[WPT];
+    bool alive[WPT];
 #pragma unroll
-    for (int k = 0; k < CAS_WPT; ++k) {
-        const int idx = tid + k * CAS_THREADS;
+    for (int k = 0; k < WPT; ++k) {
+        const int idx = tid + k * THREADS;
         alive[k] = idx < nwin;
         const int lr = alive[k] ? idx / cols_valid : 0, lc = alive[k] ? idx - lr * cols_valid : 0;
         wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
         hs[k] = 0.f;
     }
 
-    int n_slots = nwin, n_alive = nwin, t = 0, round = 0;
+    // slot idx = tid + k*stride; after a re-pack the survivors are spread over as few warps as possible (4 slots per
+    // thread) so the per-stage overhead is shared by 4 windows, and the warps left without slots retire
+    int n_slots = nwin, n_alive = nwin, t = 0, round = 0, stride = THREADS;
     unsigned my_weak = 0;
     while (t < p.T && n_alive > 0) {
         // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
-        const int t_end = min(p.T, t + (n_slots > CAS_THREADS ? 8 : (n_slots > 64 ? 16 : 32)));
+        const int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
         bool mine = false;
 #pragma unroll
-        for (int k = 0; k < CAS_WPT; ++k) mine |= alive[k];
+        for (int k = 0; k < WPT; ++k) mine |= alive[k];
         if (__any_sync(0xffffffffu, mine)) {
-            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*CAS_THREADS < n_slots (warp-uniform)
+            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (first + 2 * CAS_THREADS < n_slots) run_round<D2, 4>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + CAS_THREADS < n_slots) run_round<D2, 2>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else run_round<D2, 1>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else run_round<D2, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
         }
         // ---- how many windows of the tile are still alive
-        unsigned bal[CAS_WPT];
+        unsigned bal[WPT];
         int wcnt = 0;
 #pragma unroll
-        for (int k = 0; k < CAS_WPT; ++k) {
+        for (int k = 0; k < WPT; ++k) {
             bal[k] = __ballot_sync(0xffffffffu, alive[k]);
             wcnt += __popc(bal[k]);
         }
@@ -229,47 +242,59 @@ __global__ void __launch_bounds__(CAS_THREADS) cascade_kernel(const CascadeParam
         t = t_end;
         ++round;
         if (n_alive == 0 || t >= p.T) break;
-        if (n_alive * 3 > n_slots || n_slots <= 32) continue;
+        if (n_alive * p.compact_den > n_slots * p.compact_num || n_slots <= 32 || n_alive > p.list_cap) continue;
 
         // ---- order-preserving re-pack of the CTA's survivors into the first n_alive slots
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < CAS_WPT; ++k) s_tot[k * (CAS_THREADS / 32) + warp] = __popc(bal[k]);
+            for (int k = 0; k < WPT; ++k) s_tot[k * WARPS + warp] = __popc(bal[k]);
         }
         __syncthreads();
         if (warp == 0) {
-            const int val = s_tot[lane];
-            int inc = val;
+            int v_[EPL], sum = 0;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { v_[e] = s_tot[lane * EPL + e]; sum += v_[e]; }
+            int inc = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += o;
             }
-            s_tot[lane] = inc - val;
+            int run = inc - sum;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { s_pre[lane * EPL + e] = run; run += v_[e]; }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < CAS_WPT; ++k) {
+        for (int k = 0; k < WPT; ++k) {
             if (alive[k]) {
-                const int pos = s_tot[k * (CAS_THREADS / 32) + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+                const int pos = s_pre[k * WARPS + warp] + __popc(bal[k] & ((1u << lane) - 1u));
                 s_woff[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
                 s_score[pos] = hs[k];
             }
         }
         __syncthreads();
         n_slots = n_alive;
+        stride = (p.flags & 2) ? THREADS : min(THREADS, (((n_slots + 3) >> 2) + 31) & ~31);
 #pragma unroll
-        for (int k = 0; k < CAS_WPT; ++k) {
-            const int idx = tid + k * CAS_THREADS;
-            alive[k] = idx < n_slots;
+        for (int k = 0; k < WPT; ++k) {
+            const int idx = tid + k * stride;
+            alive[k] = k < 4 && tid < stride && idx < n_slots;
             wa[k] = tile_base + 4u * (alive[k] ? (unsigned)s_woff[idx] : 0u);
             hs[k] = alive[k] ? s_score[idx] : 0.f;
         }
+        // warps left without slots retire; warp 0 (which never retires and takes part in every later barrier)
+        // clears their counts so that later re-packs see 0 for them
+        if (warp == 0) {
+            for (int e = lane; e < ENTRIES; e += 32)
+                if ((e % WARPS) * 32 >= stride) s_tot[e] = 0;
+        }
+        if (tid >= stride && !(p.flags & 1)) break;
     }
 
     // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
 #pragma unroll
-    for (int k = 0; k < CAS_WPT; ++k) {
+    for (int k = 0; k < WPT; ++k) {
         if (alive[k]) {
             const int wo = (int)((wa[k] - tile_base) >> 2);
             const int lr = wo / pitch, lc = wo - lr * pitch;
@@ -476,17 +501,26 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
 
     const long long grid = (long long)tiles_per_frame * batch;
     WBG_REQUIRE(grid <= 0x7fffffffLL, "cascade: too many tiles (%lld)", grid);
-    const int smem = model->geom.smem_bytes;
-    if (model->all_d2) {
+    const CascadeGeom& g = model->geom;
+    p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
+    p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
+    { const char* f = getenv("WBG_CAS_FLAGS"); p.flags = f ? atoi(f) : 0; }
+    const int smem = g.smem_bytes;
+    if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
-        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);
-        cascade_kernel<true><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
+#define WBG_CAS_LAUNCH(D2V, TH, WP)                                                                                          \
+    do {                                                                                                                     \
+        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<D2V, TH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);                                                                     \
+        cascade_kernel<D2V, TH, WP><<<(unsigned)grid, TH, smem, stream>>>(p);                                                \
+    } while (0)
+    if (g.threads == 512 && g.wpt == 8) {
+        if (model->all_d2) WBG_CAS_LAUNCH(true, 512, 8); else WBG_CAS_LAUNCH(false, 512, 8);
     } else {
-        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);
-        cascade_kernel<false><<<(unsigned)grid, CAS_THREADS, smem, stream>>>(p);
+        WBG_REQUIRE(g.threads == 256 && g.wpt == 4, "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
+        if (model->all_d2) WBG_CAS_LAUNCH(true, 256, 4); else WBG_CAS_LAUNCH(false, 256, 4);
     }
+#undef WBG_CAS_LAUNCH
     wbg_prof_end(WBG_PROF_CASCADE_KERNEL, stream);
     WBG_CUDA_TRY(cudaGetLastError());
 

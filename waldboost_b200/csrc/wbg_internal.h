@@ -40,10 +40,11 @@ struct CascadeGeom {
     int rows, pitch;   // patch rows, padded row pitch (floats)
     int plane;         // floats per channel plane
     int smem_bytes;    // dynamic shared memory of the cascade kernel
+    int threads, wpt;  // CTA size and window slots per thread: threads * wpt >= TR * TC
+    int list_cap;      // capacity of the re-pack lists (windows): threads * wpt / 2
+    int compact_num, compact_den;   // re-pack when alive * den <= slots * num   (num/den <= 1/2)
+    int round_full, round_mid, round_tail;   // stages per round while slots > threads / > 64 / else
 };
-constexpr int CAS_THREADS = 256;
-constexpr int CAS_WPT = 4;                       // window slots per thread
-constexpr int CAS_MAX_WIN = CAS_THREADS * CAS_WPT;  // windows per tile upper bound
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g);
 
 // Device-side description of one pyramid level (superset of wbg_level).
