@@ -343,7 +343,11 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
             const int a = Lf[0], b = Rt[0];
             if (Lf[a] >= 0 && Lf[b] >= 0) {
                 const int ll = Lf[a], lr = Rt[a], rl = Lf[b], rr = Rt[b];
-                if (Lf[ll] < 0 && Lf[lr] < 0 && Lf[rl] < 0 && Lf[rr] < 0) {
+                // the fast path marks rejected windows with a NaN score, so live scores must never be NaN: it needs
+                // finite predictions (a float32 sum of finite terms can overflow to inf but never becomes NaN
+                // unless +inf and -inf meet, which the finite-threshold test below also rules out in practice)
+                const bool finite = isfinite(P[ll]) && isfinite(P[lr]) && isfinite(P[rl]) && isfinite(P[rr]);
+                if (finite && Lf[ll] < 0 && Lf[lr] < 0 && Lf[rl] < 0 && Lf[rr] < 0) {
                     StageD2& s = d2[t];
                     const NodeDev* nd = &nodes[(size_t)t * N];
                     // byte offsets inside the planar shared-memory patch

@@ -80,14 +80,18 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
 // the warp is live).  `last[k]` is the index after the last stage the slot entered alive (n_weak, model.py:252).
 // Generic topology: follow the left/right links of the node records (training.py:88-95).
 template <bool D2, int NK, int WPT>
-__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], bool (&alive)[WPT],
-                                          int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
+__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], int t, int t_end,
+                                          unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
                                           const float* __restrict__ thetas) {
+    // A rejected window is marked by hs = NaN: NaN + p stays NaN and NaN >= theta is false for every theta
+    // (including -inf = "no test", model.py:253), so dead slots need no flag.  Live scores are never NaN because
+    // the depth-2 fast path is only taken for models whose predictions are all finite (wbg_model_create).
     if (D2) {
-        int last[NK];
+        int passed[NK];                 // index after the last stage whose test the slot passed
+        bool live0[NK];
 #pragma unroll
-        for (int k = 0; k < NK; ++k) last[k] = t;
-#pragma unroll 2
+        for (int k = 0; k < NK; ++k) { passed[k] = t; live0[k] = hs[k] == hs[k]; }
+#pragma unroll 4
         for (int s = t; s < t_end; ++s) {
             const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
             const int4 A = rec[0], B = rec[1], Cc = rec[2];
@@ -95,31 +99,28 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             const float p2 = __int_as_float(B.z), p3 = __int_as_float(B.w);
             const float p5 = __int_as_float(Cc.x), p6 = __int_as_float(Cc.y), theta = __int_as_float(Cc.z);
             const int s1 = s + 1;
-            constexpr int G = NK < 4 ? NK : 4;               // slots in flight together (bounds live registers)
+            float x0[NK], xa[NK], xb[NK];
 #pragma unroll
-            for (int g = 0; g < NK; g += G) {
-                float x0[G], xa[G], xb[G];
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    x0[k] = lds_f32(wa[g + k] + (unsigned)A.x);
-                    xa[k] = lds_f32(wa[g + k] + (unsigned)A.z);
-                    xb[k] = lds_f32(wa[g + k] + (unsigned)B.x);
-                }
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    const float pa = (xa[k] <= thr1) ? p2 : p3;    // training.py:92 -- left iff X <= threshold
-                    const float pb = (xb[k] <= thr4) ? p5 : p6;
-                    hs[g + k] += (x0[k] <= thr0) ? pa : pb;        // float32 accumulation in stage order (model.py:251)
-                    last[g + k] = alive[g + k] ? s1 : last[g + k];
-                }
+            for (int k = 0; k < NK; ++k) {
+                x0[k] = lds_f32(wa[k] + (unsigned)A.x);
+                xa[k] = lds_f32(wa[k] + (unsigned)A.z);
+                xb[k] = lds_f32(wa[k] + (unsigned)B.x);
             }
-            if (theta != -CUDART_INF_F) {                      // model.py:253 -- theta == -inf: no test at this stage
 #pragma unroll
-                for (int k = 0; k < NK; ++k) alive[k] = alive[k] && hs[k] >= theta;   // model.py:255-258
+            for (int k = 0; k < NK; ++k) {
+                const float pa = (xa[k] <= thr1) ? p2 : p3;        // training.py:92 -- left iff X <= threshold
+                const float pb = (xb[k] <= thr4) ? p5 : p6;
+                const float h = hs[k] + ((x0[k] <= thr0) ? pa : pb);   // float32 accumulation in stage order (model.py:251)
+                const bool ok = h >= theta;                        // model.py:255; true for every live score when theta = -inf
+                hs[k] = ok ? h : CUDART_NAN_F;
+                passed[k] = ok ? s1 : passed[k];
             }
         }
+        // model.py:252 -- n_weak += windows entering each stage: a slot that entered the round alive ran the stages it
+        // passed plus the one that rejected it
 #pragma unroll
-        for (int k = 0; k < NK; ++k) my_weak += (unsigned)(last[k] - t);
+        for (int k = 0; k < NK; ++k)
+            my_weak += live0[k] ? (unsigned)(passed[k] - t + ((hs[k] == hs[k]) ? 0 : 1)) : 0u;
     } else {
         const float* tile = nullptr;
         asm("cvta.shared.u64 %0, %1;" : "=l"(tile) : "l"((unsigned long long)tile_base));
@@ -129,16 +130,16 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             const bool test = theta != -CUDART_INF_F;
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
-                if (alive[k]) {
+                if (hs[k] == hs[k]) {
                     const float* w = tile + ((wa[k] - tile_base) >> 2);
                     NodeDev nd = load_node(nb);
                     while (nd.left >= 0) {
                         const float x = w[nd.off];
                         nd = load_node(nb + ((x <= nd.thr) ? nd.left : nd.right));
                     }
-                    hs[k] += nd.pred;
+                    const float h = hs[k] + nd.pred;
                     ++my_weak;
-                    alive[k] = !test || hs[k] >= theta;
+                    hs[k] = (!test || h >= theta) ? h : CUDART_NAN_F;
                 }
             }
         }
@@ -197,15 +198,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kerne
     unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
     asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
     unsigned wa[WPT];
-    float hs[WPT];
-    bool alive[WPT];
+    float hs[WPT];                     // running score of the slot's window; NaN = no window / rejected
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
         const int idx = tid + k * THREADS;
-        alive[k] = idx < nwin;
-        const int lr = alive[k] ? idx / cols_valid : 0, lc = alive[k] ? idx - lr * cols_valid : 0;
+        const bool has = idx < nwin;
+        const int lr = has ? idx / cols_valid : 0, lc = has ? idx - lr * cols_valid : 0;
         wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
-        hs[k] = 0.f;
+        hs[k] = has ? 0.f : CUDART_NAN_F;
     }
 
     // slot idx = tid + k*stride; after a re-pack the survivors are spread over as few warps as possible (4 slots per
@@ -217,21 +217,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kerne
         const int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
         bool mine = false;
 #pragma unroll
-        for (int k = 0; k < WPT; ++k) mine |= alive[k];
+        for (int k = 0; k < WPT; ++k) mine |= hs[k] == hs[k];
         if (__any_sync(0xffffffffu, mine)) {
             // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else run_round<D2, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else run_round<D2, 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
         }
         // ---- how many windows of the tile are still alive
         unsigned bal[WPT];
         int wcnt = 0;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            bal[k] = __ballot_sync(0xffffffffu, alive[k]);
+            bal[k] = __ballot_sync(0xffffffffu, hs[k] == hs[k]);
             wcnt += __popc(bal[k]);
         }
         const int par = round % 3;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kerne
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            if (alive[k]) {
+            if (hs[k] == hs[k]) {
                 const int pos = s_pre[k * WARPS + warp] + __popc(bal[k] & ((1u << lane) - 1u));
                 s_woff[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
                 s_score[pos] = hs[k];
@@ -275,27 +275,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kerne
         }
         __syncthreads();
         n_slots = n_alive;
-        stride = (p.flags & 2) ? THREADS : min(THREADS, (((n_slots + 3) >> 2) + 31) & ~31);
+        stride = (p.flags & 2) ? min(THREADS, (((n_slots + 3) >> 2) + 31) & ~31) : THREADS;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const int idx = tid + k * stride;
-            alive[k] = k < 4 && tid < stride && idx < n_slots;
-            wa[k] = tile_base + 4u * (alive[k] ? (unsigned)s_woff[idx] : 0u);
-            hs[k] = alive[k] ? s_score[idx] : 0.f;
+            const bool has = k < 4 && tid < stride && idx < n_slots;
+            wa[k] = tile_base + 4u * (has ? (unsigned)s_woff[idx] : 0u);
+            hs[k] = has ? s_score[idx] : CUDART_NAN_F;
         }
-        // warps left without slots retire; warp 0 (which never retires and takes part in every later barrier)
-        // clears their counts so that later re-packs see 0 for them
-        if (warp == 0) {
-            for (int e = lane; e < ENTRIES; e += 32)
-                if ((e % WARPS) * 32 >= stride) s_tot[e] = 0;
-        }
-        if (tid >= stride && !(p.flags & 1)) break;
     }
 
     // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
-        if (alive[k]) {
+        if (hs[k] == hs[k]) {
             const int wo = (int)((wa[k] - tile_base) >> 2);
             const int lr = wo / pitch, lc = wo - lr * pitch;
             const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
