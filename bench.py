@@ -40,9 +40,13 @@ UNIT = "frames/s"
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference path
+CPU_GROUP = 4      # worker processes sharing one frame (its pyramid levels are split between them, largest level = 16 %)
+
+
 def _cpu_worker(job):
-    """One worker process: oracle detect() on `n` 1080p frames (seed0 ..).  Imports the oracle only here."""
-    seed0, n, profile, h, w = job
+    """One worker process: oracle detect() on the given pyramid levels of one 1080p frame.  The oracle is imported
+    only here (CPU baseline / reference arm)."""
+    seed, levels, profile, h, w = job
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -54,11 +58,9 @@ def _cpu_worker(job):
     if profile == "dense":
         M.theta = [-np.inf] * len(M)
     Cs = oracle_cascade(M)
-    frames = [S.synthetic_frame(seed0 + i, h, w) for i in range(n)]
+    frame = S.synthetic_frame(seed, h, w)
     t0 = time.perf_counter()
-    hits = 0
-    for f in frames:
-        hits += Cs.detect(f)[1].size
+    hits = Cs.detect(frame, levels)[1].size
     return time.perf_counter() - t0, hits, Cs.n_loc, Cs.n_weak
 
 
@@ -70,21 +72,35 @@ def host_cores():
 
 
 class CpuPool:
-    """Image-sharded worker processes (the reference's own parallel pattern: multiprocessing.Pool over files,
-    scripts/waldboost-detect.py:65), spawned so they never inherit a CUDA context."""
+    """Worker processes over frames (the reference's own parallel pattern: multiprocessing.Pool over files,
+    scripts/waldboost-detect.py:65); to keep a step short every frame is additionally split by pyramid level over
+    CPU_GROUP workers (levels are independent, channels.py:125-132).  Spawned, so no CUDA context is inherited."""
 
     def __init__(self, workers):
         import multiprocessing as mp
-        self.workers = workers
-        self.pool = mp.get_context("spawn").Pool(workers)
+        self.group = min(CPU_GROUP, workers)
+        self.frames = max(1, workers // self.group)
+        self.workers = self.frames * self.group
+        self.pool = mp.get_context("spawn").Pool(self.workers)
 
-    def step(self, frames_per_worker, profile, h=H, w=W, seed0=1000):
-        jobs = [(seed0 + k * frames_per_worker, frames_per_worker, profile, h, w) for k in range(self.workers)]
-        t0 = time.perf_counter()
+    def _level_shards(self, h, w):
+        import waldboost_b200 as wb
+        from waldboost_b200.engine import plan_geometry
+        from waldboost_b200.sharding import assign_levels
+        M = wb.Model.load(MODEL_B)
+        plan = plan_geometry(h, w, M.channel_opts, M._spec(), int(M.shape[0]), int(M.shape[1]))
+        return assign_levels([lv.u * lv.v for lv in plan.levels], self.group)
+
+    def step(self, profile, h=H, w=W, seed0=1000):
+        shards = self._level_shards(h, w)
+        jobs = [(seed0 + f, shards[g], profile, h, w) for f in range(self.frames) for g in range(self.group)]
         res = self.pool.map(_cpu_worker, jobs, chunksize=1)
-        wall = time.perf_counter() - t0
-        busy = max(r[0] for r in res)            # exclude process start-up / frame synthesis: slowest worker's detect time
-        return wall, busy, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
+        busy = max(r[0] for r in res)            # slowest worker's detect time (excludes start-up and frame synthesis)
+        return self.frames, busy, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
+
+    def sample(self):
+        return (f"{self.frames} frames of 1920x1080 per step on {self.workers} worker processes "
+                f"(each frame's 64 pyramid levels split over {self.group} workers), oracle/wb_oracle.py Cascade.detect")
 
     def close(self):
         self.pool.close()
@@ -98,23 +114,23 @@ def run_reference(args):
     cores = max(1, min(host_cores(), args.cpu_workers or 10 ** 6))
     pool = CpuPool(cores)
     for _ in range(args.warmup):                 # untimed: a small frame per worker (imports, page-in; there is no JIT)
-        pool.step(1, args.profile, 135, 240)
+        pool.step(args.profile, 135, 240)
     t = 0.0
     frames = 0
     for _ in range(args.steps):
-        _, busy, _, _, _ = pool.step(1, args.profile)
+        n, busy, _, _, _ = pool.step(args.profile)
         t += busy
-        frames += cores
+        frames += n
     pool.close()
     fps = frames / t
-    sample = f"{cores} frames of 1920x1080 per step (one per worker process), {args.steps} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Model.detect, 1920x1080 uint8 frames, 12x12x4 grad_hist model, 1024 depth-2 stages, {args.profile} thetas",
                    "profile": args.profile},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                         "sample": pool.sample() + f", {args.steps} steps"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,14 +233,13 @@ def run_gpu(args):
     # ---- CPU baseline first (rank 0 at N=1 only), before this process's CUDA work starts: bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = max(1, min(host_cores(), args.cpu_workers or 32))
+        cores = max(1, min(host_cores(), args.cpu_workers or 64))
         pool = CpuPool(cores)
-        pool.step(1, args.profile, 135, 240)
-        _, busy, _, n_loc_c, n_weak_c = pool.step(1, args.profile)
+        pool.step(args.profile, 135, 240)
+        n_fr, busy, _, n_loc_c, n_weak_c = pool.step(args.profile)
         pool.close()
-        cpu = {"value": cores / busy, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} frames of 1920x1080 (one per worker process), oracle/wb_oracle.py Cascade.detect, "
-                         f"eval_cost {n_weak_c / max(n_loc_c, 1):.1f}, {busy:.1f} s"}
+        cpu = {"value": n_fr / busy, "unit": UNIT, "cores": pool.workers, "kind": "port",
+               "sample": pool.sample() + f", eval_cost {n_weak_c / max(n_loc_c, 1):.1f}, {busy:.1f} s"}
 
     from waldboost_b200.build import build
     if local == 0:

@@ -223,8 +223,10 @@ def resize_bilinear(base, nh, nw):
     return out.astype(dtype)        # uint8: truncation toward zero
 
 
-def channel_pyramid(image, channel_opts):
-    """channels.py:111-146.  `channel_opts["channels"]` is a callable im -> (h, w, C) float32."""
+def channel_pyramid(image, channel_opts, levels=None):
+    """channels.py:111-146.  `channel_opts["channels"]` is a callable im -> (h, w, C) float32.
+    `levels` (not in the reference): if given, only the pyramid levels with these indices are computed and yielded
+    (every level depends only on the original image) -- used to spread one frame over several CPU workers."""
     if not isinstance(image, np.ndarray):
         raise TypeError("Image must be numpy array")
     if image.ndim != 2:
@@ -234,9 +236,13 @@ def channel_pyramid(image, channel_opts):
     smooth = channel_opts["smooth"]
     channels = channel_opts["channels"]
     assert shrink in [1, 2], "Shrink factor must be integer 1 <= shrink <= 2"
+    index = -1
     for base in image_octaves(image):
         h, w = base.shape[:2]
         for i in range(n_per_oct):
+            index += 1
+            if levels is not None and index not in levels:
+                continue
             nh, nw = level_size(h, w, i, n_per_oct, shrink)
             real_scale = nw / image.shape[1]
             im = resize_bilinear(base, nh, nw)
@@ -321,9 +327,9 @@ class Cascade:
         self.n_loc = 0
         self.n_weak = 0
 
-    def channels(self, image):
+    def channels(self, image, levels=None):
         """model.py:95-103."""
-        yield from channel_pyramid(image, self.channel_opts)
+        yield from channel_pyramid(image, self.channel_opts, levels)
 
     def predict_on_image(self, X, trace=None):
         """model.py:216-259.  Window grid is (u-m) x (v-n) (model.py:243); scores accumulate in float32 in stage
@@ -366,10 +372,12 @@ class Cascade:
         for chns, scale in self.channels(image):
             yield chns, scale, self.predict_on_image(chns)
 
-    def detect(self, image):
-        """model.py:149-179 -> (boxes [K,4] f32, scores [K] f32, level [K] i32) in (level, r, c) order."""
-        B, S, L = [], [], []
-        for lvl, (chns, scale) in enumerate(self.channels(image)):
+    def detect(self, image, levels=None):
+        """model.py:149-179 -> (boxes [K,4] f32, scores [K] f32, level [K] i32) in (level, r, c) order.
+        `levels`: optional sorted list of pyramid level indices to restrict the scan to (see channel_pyramid)."""
+        B, S, L = [np.empty((0, 4), F32)], [np.empty(0, F32)], [np.empty(0, np.int32)]
+        ids = range(10 ** 9) if levels is None else sorted(levels)
+        for lvl, (chns, scale) in zip(ids, self.channels(image, levels)):
             r, c, h = self.predict_on_image(chns)
             B.append(self.get_boxes(r, c, scale))
             S.append(h)
