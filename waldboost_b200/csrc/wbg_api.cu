@@ -164,7 +164,7 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
     // channels.py:124-131 -- Python double arithmetic: factor = 2**(-1/n); s = factor**i; int((w*s)/shrink)*shrink
     const double factor = ::pow(2.0, -1.0 / (double)npo);
     long long chn = 0, win = 0, nloc = 0;
-    int ptile = 0, ctile = 0;
+    int ptile = 0, ctile = 0, qtile = 0;
     for (size_t k = 0; k < p->octaves.size(); ++k) {
         const int h = p->octaves[k].h, w = p->octaves[k].w;
         for (int i = 0; i < npo; ++i) {
@@ -199,6 +199,9 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
             D.ptiles_x = (L.v + PYR_TV - 1) / PYR_TV;
             D.ptiles_y = (L.u + PYR_TU - 1) / PYR_TU;
             ptile += D.ptiles_x * D.ptiles_y;
+            D.qtile0 = qtile;
+            D.qtiles_x = (L.v + PYR_QTV - 1) / PYR_QTV;
+            qtile += D.qtiles_x * ((L.u + PYR_QTU - 1) / PYR_QTU);
             D.ctile0 = ctile;
             if (p->geom_ok && nwin > 0) {
                 D.ctiles_x = (L.win_cols + p->geom.TC - 1) / p->geom.TC;
@@ -212,7 +215,7 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
             p->dev_levels.push_back(D);
         }
     }
-    p->chn_floats = chn; p->windows = win; p->n_loc = nloc; p->ptiles = ptile; p->ctiles = ctile;
+    p->chn_floats = chn; p->windows = win; p->n_loc = nloc; p->ptiles = ptile; p->ctiles = ctile; p->qtiles = qtile;
 
     if (device_tables && !p->dev_levels.empty()) {
         cudaError_t e = cudaGetDevice(&p->device);

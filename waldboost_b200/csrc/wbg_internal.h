@@ -33,6 +33,7 @@ static inline size_t wbg_align_up(size_t x, size_t a) { return (x + a - 1) / a *
 constexpr int PYR_TU = 16;
 constexpr int PYR_TV = 32;
 constexpr int PYR_THREADS = 256;
+constexpr int PYR_QTU = 16, PYR_QTV = 29;       // tile of level_hist4_u8_kernel
 
 // Tile of the cascade kernel: TR x TC windows, channel patch (TR+m-1) x (TC+n-1) x C staged planar in smem.
 struct CascadeGeom {
@@ -55,6 +56,7 @@ struct LevelDev {
     long long win_off;   // first window slot of this level inside one frame (multiple of 32)
     int win_rows, win_cols;
     int ptile0, ptiles_x, ptiles_y;   // tiles of the channel kernel (prefix, grid)
+    int qtile0, qtiles_x;             // 16 x 29 tiles of the 4-bin uint8 channel kernel
     int ctile0, ctiles_x, ctiles_y;   // tiles of the cascade kernel
     float inv_scale;                  // float32(1 / scale), model.py:147
     int pad_;
@@ -73,7 +75,7 @@ struct wbg_plan {
     std::vector<wbg_level> levels;
     std::vector<LevelDev> dev_levels;
     long long chn_floats = 0, octave_elems = 0, windows = 0, n_loc = 0;
-    int ptiles = 0, ctiles = 0;  // tiles per frame
+    int ptiles = 0, ctiles = 0, qtiles = 0;  // tiles per frame
     CascadeGeom geom{};
     bool geom_ok = false;
     int device = -1;

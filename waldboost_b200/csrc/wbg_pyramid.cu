@@ -12,6 +12,7 @@
 //                     (channels.py:132-142) through shared memory, reading the octave image and writing the
 //                     channel map exactly once.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "wbg_internal.h"
 
@@ -532,6 +533,210 @@ __global__ void __launch_bounds__(PYR_THREADS) level_hist_kernel(const PyrParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 4-bin uint8 kernel
+// The configuration every BASELINE config but C runs: uint8 frames, grad_hist with the default 4 unsigned bins and
+// no bias, shrink 2, smooth 1.  Same results as level_hist_kernel, bit for bit, with far fewer instructions:
+//   * the tile is 16 x 29 pooled pixels so that a row of the resized tile is exactly 64 pixels = 2 warp-wide chunks;
+//     every phase hands whole rows to warps (no integer division, row data is warp-uniform);
+//   * uint8 -> float32 and float32 -> floor go through magic-constant adds instead of the conversion pipe;
+//   * bins 0 and 2 are |gx| and |gy| (cos/sin = 1, 0 and 6.1e-17, 1): small integers, so pooling and smoothing them in
+//     float32 is exact -- no float64 at all.  The only exception, a smoothed |gy| sum of exactly 0 next to non-zero
+//     gx (the reference then yields ~1e-14 from gx*6.1e-17), is recomputed with the reference's float64 expression;
+//   * bins 1 and 3 keep NumPy's float64 projection and Numba's float64 smoothing.
+constexpr int H4_TU = 16, H4_TV = 29, H4_WARPS = 9, H4_THREADS = 32 * H4_WARPS;
+constexpr int H4_PH = H4_TU + 2, H4_PW = H4_TV + 2, H4_RH = 2 * H4_PH + 2, H4_RW = 2 * H4_PW + 2;   // 18, 31, 38, 64
+static_assert(H4_RW == 64, "a resized tile row must be two warp-wide chunks");
+
+__device__ __forceinline__ float u8_to_f32(unsigned q) { return __int_as_float(0x4B000000u | q) - 8388608.f; }
+
+// reference arithmetic for one smoothed bin-2 value (rare path, see above): channels.py:50, :61-64, :78-83
+__device__ __noinline__ float hist4_exact_bin2(const float* __restrict__ s_R, int oy, int ox, double c2, double s2) {
+    double pooled[9];
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+        const int py = oy + k / 3, px = ox + k % 3;            // pooled coordinates inside the halo tile
+        float acc = 0.f;
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {
+            const int fy = 2 * py + (sub & 1) + 1, fx = 2 * px + (sub >> 1) + 1;     // R-grid position of the pixel
+            const float* r = s_R + fy * H4_RW + fx;
+            const float gx = (fmaf(2.f, r[-1], r[-1 - H4_RW] + r[-1 + H4_RW])) - (fmaf(2.f, r[1], r[1 - H4_RW] + r[1 + H4_RW]));
+            const float gy = (fmaf(2.f, r[-H4_RW], r[-H4_RW - 1] + r[-H4_RW + 1])) - (fmaf(2.f, r[H4_RW], r[H4_RW - 1] + r[H4_RW + 1]));
+            const float ch = (float)__dadd_rn(__dmul_rn((double)gx, c2), -__dmul_rn((double)gy, s2));
+            acc = sub == 0 ? fabsf(ch) : __fadd_rn(acc, fabsf(ch));
+        }
+        pooled[k] = (double)__fmul_rn(acc, 0.25f);
+    }
+    double a = pooled[0] + 2.0 * pooled[1];
+    a += pooled[2];
+    a += 2.0 * pooled[3];
+    a += 4.0 * pooled[4];
+    a += 2.0 * pooled[5];
+    a += pooled[6];
+    a += 2.0 * pooled[7];
+    a += pooled[8];
+    return (float)(a / 16.0);
+}
+
+__global__ void __launch_bounds__(H4_THREADS) level_hist4_u8_kernel(const PyrParams p) {
+    constexpr int PH = H4_PH, PW = H4_PW, RH = H4_RH, RW = H4_RW;
+    __shared__ __align__(16) TapF s_tapr[RH];
+    __shared__ __align__(16) TapF s_tapc[RW];
+    __shared__ __align__(16) float s_R[RH * RW];
+    __shared__ __align__(16) float2 s_P02[PH * PW];     // pooled bins 0 and 2 (exact in float32)
+    __shared__ __align__(16) double2 s_P13[PH * PW];    // pooled bins 1 and 3 as float64 for the smoothing sums
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    int lo = 0, hi = p.n_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.levels[mid].qtile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const LevelDev* __restrict__ L = p.levels + lo;
+    const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
+    const int local = tile_id - L->qtile0;
+    const int ty = local / L->qtiles_x, tx = local - ty * L->qtiles_x;
+    const int ou0 = ty * H4_TU, ov0 = tx * H4_TV;
+    const int ry0 = 2 * (ou0 - 1) - 1, rx0 = 2 * (ov0 - 1) - 1;
+    const uint8_t* __restrict__ src = (L->oct == 0)
+        ? reinterpret_cast<const uint8_t*>(p.img) + (long long)frame * p.img_stride
+        : reinterpret_cast<const uint8_t*>(p.oct_ws) + (long long)frame * p.oct_stride + L->src_off;
+    const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
+    const bool identity = L->identity != 0;
+
+    // ---- P0: bilinear taps of the tile's rows and columns (reflect-extended resized coordinates)
+    if (tid < RH + RW) {
+        const bool row = tid < RH;
+        const Tap t = row ? make_tap(reflect_idx(ry0 + tid, nh), L->zoom_r, sh) : make_tap(reflect_idx(rx0 + (tid - RH), nw), L->zoom_c, sw);
+        TapF f;
+        f.i0 = t.i0; f.i1 = t.i1; f.w1f = (float)t.w1; f.pad_ = 0.f; f.w0 = t.w0; f.w1 = t.w1;
+        if (row) s_tapr[tid] = f; else s_tapc[tid - RH] = f;
+    }
+    __syncthreads();
+
+    // ---- P1: resized tile (channels.py:132), one (row, 32-column chunk) per warp iteration
+    for (int task = warp; task < 2 * RH; task += H4_WARPS) {
+        const int iy = task >> 1, ix = ((task & 1) << 5) + lane;
+        const TapF* a = s_tapr + iy;
+        const TapF* b = s_tapc + ix;
+        const uint8_t* __restrict__ r0p = src + (long long)a->i0 * sw;
+        const uint8_t* __restrict__ r1p = src + (long long)a->i1 * sw;
+        const int bi0 = b->i0, bi1 = b->i1;
+        float val;
+        if (identity) {
+            val = u8_to_f32(__ldg(r0p + bi0));
+        } else {
+            const unsigned q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
+            const float f00 = u8_to_f32(q00), f01 = u8_to_f32(q01), f10 = u8_to_f32(q10), f11 = u8_to_f32(q11);
+            const float wx = b->w1f, wy = a->w1f;
+            const float top = fmaf(wx, f01 - f00, f00), bot = fmaf(wx, f11 - f10, f10);
+            const float r = fmaf(wy, bot - top, top);
+            val = __fadd_rd(r, 12582912.f) - 12582912.f;            // floor(r) for |r| < 2^22
+            const float fr = r - val;
+            // the float32 estimate is within 1e-4 of scipy's float64 sum: away from an integer both truncate alike
+            if (fabsf(fr - 0.5f) > 0.5f - RESAMPLE_DELTA) {
+                if ((q00 | q01 | q10 | q11) == 0u) {
+                    val = 0.f;
+                } else {
+                    const double w0r = a->w0, w1r = a->w1, w0c = b->w0, w1c = b->w1;
+                    double t = __dmul_rn(__dmul_rn((double)q00, w0r), w0c);
+                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, w0r), w1c));
+                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, w1r), w0c));
+                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, w1r), w1c));
+                    val = finish_resample<uint8_t>(t, mm.x, mm.y);
+                }
+            }
+        }
+        s_R[iy * RW + ix] = val;
+    }
+    __syncthreads();
+
+    // ---- P2: gradients, bins, 2x2 mean; one pooled row per warp iteration, one pooled pixel per lane
+    const double c1 = p.cs[1], s1 = p.sn[1], c3 = p.cs[3], s3 = p.sn[3];
+    for (int py = warp; py < PH; py += H4_WARPS) {
+        const int px = lane;
+        const int pu = ou0 - 1 + py, pv = ov0 - 1 + px;
+        if (px >= PW || pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
+        float R[4][4];
+        const float* rp = s_R + (2 * py) * RW + 2 * px;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float2 x0 = *reinterpret_cast<const float2*>(rp + a * RW);
+            const float2 x1 = *reinterpret_cast<const float2*>(rp + a * RW + 2);
+            R[a][0] = x0.x; R[a][1] = x0.y; R[a][2] = x1.x; R[a][3] = x1.y;
+        }
+        // channels.py:16-21 on small integers: every float32 operation below is exact
+        float gx[2][2], gy[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            float V[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) V[b] = fmaf(2.f, R[a + 1][b], R[a][b] + R[a + 2][b]);
+            gx[a][0] = V[0] - V[2];
+            gx[a][1] = V[1] - V[3];
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            float Hh[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) Hh[a] = fmaf(2.f, R[a][b + 1], R[a][b] + R[a][b + 2]);
+            gy[0][b] = Hh[0] - Hh[2];
+            gy[1][b] = Hh[1] - Hh[3];
+        }
+        // pooling order of channels.py:61-64: a00, a10 (next row), a01 (next column), a11
+        const float a0 = ((fabsf(gx[0][0]) + fabsf(gx[1][0])) + fabsf(gx[0][1])) + fabsf(gx[1][1]);
+        const float a2 = ((fabsf(gy[0][0]) + fabsf(gy[1][0])) + fabsf(gy[0][1])) + fabsf(gy[1][1]);
+        float ch1[2][2], ch3[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const double gxd = (double)gx[a][b], gyd = (double)gy[a][b];
+                // channels.py:50 under NumPy 2: float64 products and difference, one rounding to float32
+                ch1[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c1), -__dmul_rn(gyd, s1)));
+                ch3[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c3), -__dmul_rn(gyd, s3)));
+            }
+        const float a1 = __fadd_rn(__fadd_rn(__fadd_rn(ch1[0][0], ch1[1][0]), ch1[0][1]), ch1[1][1]);
+        const float a3 = __fadd_rn(__fadd_rn(__fadd_rn(ch3[0][0], ch3[1][0]), ch3[0][1]), ch3[1][1]);
+        s_P02[py * PW + px] = make_float2(a0 * 0.25f, a2 * 0.25f);
+        s_P13[py * PW + px] = make_double2((double)__fmul_rn(a1, 0.25f), (double)__fmul_rn(a3, 0.25f));
+    }
+    __syncthreads();
+
+    // ---- P3: 3x3 smoothing (channels.py:78-90), zero border ring, float4 HWC store
+    float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
+    for (int oy = warp; oy < H4_TU; oy += H4_WARPS) {
+        const int ox = lane;
+        const int ou = ou0 + oy, ov = ov0 + ox;
+        if (ox >= H4_TV || ou >= u || ov >= v) continue;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1)) {
+            const float2* q = s_P02 + (oy + 1) * PW + (ox + 1);
+            const float2 m00 = q[-PW - 1], m01 = q[-PW], m02 = q[-PW + 1], m10 = q[-1], m11 = q[0], m12 = q[1];
+            const float2 m20 = q[PW - 1], m21 = q[PW], m22 = q[PW + 1];
+            // multiples of 1/4 below 2^16: every partial sum is exact, so the order is free
+            r.x = (fmaf(4.f, m11.x, fmaf(2.f, (m01.x + m10.x) + (m12.x + m21.x), (m00.x + m02.x) + (m20.x + m22.x)))) * 0.0625f;
+            r.z = (fmaf(4.f, m11.y, fmaf(2.f, (m01.y + m10.y) + (m12.y + m21.y), (m00.y + m02.y) + (m20.y + m22.y)))) * 0.0625f;
+            if (r.z == 0.f && r.x != 0.f) r.z = hist4_exact_bin2(s_R, oy, ox, p.cs[2], p.sn[2]);
+            const double2* d = s_P13 + (oy + 1) * PW + (ox + 1);
+            const double2 d00 = d[-PW - 1], d01 = d[-PW], d02 = d[-PW + 1], d10 = d[-1], d11 = d[0], d12 = d[1];
+            const double2 d20 = d[PW - 1], d21 = d[PW], d22 = d[PW + 1];
+            double a = d00.x + 2.0 * d01.x, b = d00.y + 2.0 * d01.y;       // source order of channels.py:80-82, float64
+            a += d02.x;        b += d02.y;
+            a += 2.0 * d10.x;  b += 2.0 * d10.y;
+            a += 4.0 * d11.x;  b += 4.0 * d11.y;
+            a += 2.0 * d12.x;  b += 2.0 * d12.y;
+            a += d20.x;        b += d20.y;
+            a += 2.0 * d21.x;  b += 2.0 * d21.y;
+            a += d22.x;        b += d22.y;
+            r.y = (float)(a * 0.0625);
+            r.w = (float)(b * 0.0625);
+        }
+        *reinterpret_cast<float4*>(out + ((long long)ou * v + ov) * 4) = r;
+    }
+}
+
 template <int S, int SM>
 static constexpr size_t hist_smem_bytes(int C) {
     constexpr int PH = PYR_TU + 2 * SM, PW = PYR_TV + 2 * SM, RH = S * PH + 2, RW = S * PW + 2, RWP = (RW + 1) & ~1;
@@ -621,6 +826,16 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
         // the orientation table of the default 4-bin histogram: cos/sin = (1,0), (c,s), (6.1e-17,1), (-s,c)
         p.fast4 = (o.n_bins == 4 && !o.full && o.cos_t[0] == 1.0 && o.sin_t[0] == 0.0 && o.sin_t[2] == 1.0 &&
                    o.cos_t[2] > -1e-15 && o.cos_t[2] < 1e-15) ? 1 : 0;
+        if (sizeof(T) == 1 && p.fast4 && o.bias == 0.f && o.shrink == 2 && o.smooth == 1 && !getenv("WBG_PYR_GENERIC")) {
+            const long long grid_q = (long long)plan->qtiles * batch;
+            WBG_REQUIRE(grid_q <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid_q);
+            p.tiles_per_frame = plan->qtiles;
+            wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);
+            level_hist4_u8_kernel<<<(unsigned)grid_q, H4_THREADS, 0, stream>>>(p);
+            wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);
+            WBG_CUDA_TRY(cudaGetLastError());
+            return WBG_OK;
+        }
         return launch_hist_level<T>(p, o.shrink, o.smooth == 1 ? 1 : 0, grid_h, stream);
     }
     const size_t smem = level_smem_bytes(o, plan->C);
