@@ -335,7 +335,8 @@ def run_gpu(args):
         per_launch_s = ms * 1e-3 / n
         ach = bytes_per_frame * B / per_launch_s / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic.get(name), "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
+                "traffic": (traffic[name]["bytes_per_frame"] * B) if name in traffic else None,
+                "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
                 "ms_per_launch": per_launch_s * 1e3, "peak_source": peak_src,
                 "share_of_step": ms / n / (ms_total / args.steps)}
 
