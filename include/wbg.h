@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WBG_ABI_VERSION 1
+#define WBG_ABI_VERSION 2
 
 enum { WBG_OK = 0, WBG_EINVAL = -1, WBG_ECAP = -2, WBG_ECUDA = -3, WBG_ENOMEM = -4 };
 
@@ -71,7 +71,7 @@ typedef struct wbg_level {
     int32_t u, v;         /* channel map size after shrink                                         */
     int32_t win_rows;     /* max(u-m, 0)   (model.py:243)                                          */
     int32_t win_cols;     /* max(v-n, 0)                                                           */
-    int32_t reserved;
+    int32_t skipped;      /* 1 = not part of this plan's level subset (wbg_plan_create_levels)           */
     int64_t chn_off;      /* float offset of this level inside one frame's channel block           */
     int64_t win_off;      /* index of this level's first window inside one frame (multiple of 32)  */
     double scale;         /* yielded scale = nw / W / shrink (channels.py:131,146)                 */
@@ -124,6 +124,12 @@ int wbg_device_count(void);
  * Host arithmetic only; usable without a GPU (`device_tables = 0`) to query sizes. */
 int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
                     int32_t device_tables, wbg_plan** out);
+/* Same, restricted to the pyramid levels listed in `level_ids` (ascending, unique): geometry, offsets and level
+ * indices are those of the full pyramid, but only the listed levels are computed and scanned.  Every level depends
+ * only on the original image (channels.py:95-101,125-132), so one huge frame can be spread over several GPUs by
+ * giving each a subset of the levels.  level_ids == NULL selects every level. */
+int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
+                           int32_t device_tables, const int32_t* level_ids, int32_t n_level_ids, wbg_plan** out);
 void wbg_plan_destroy(wbg_plan* plan);
 int wbg_plan_get_info(const wbg_plan* plan, wbg_plan_info* info);
 int wbg_plan_get_levels(const wbg_plan* plan, wbg_level* levels, int32_t cap);
@@ -165,6 +171,11 @@ int wbg_predict_on_image(const wbg_model* model, const float* X, int32_t u, int3
  * float32 score accumulated in stage order (`score` [K]).  Parity/diagnostic entry point. */
 int wbg_cascade_trace(const wbg_model* model, const float* X, int32_t u, int32_t v, const int32_t* rs,
                       const int32_t* cs, int64_t K, uint8_t* leaf, float* score, void* stream);
+
+/* Sample-mode cascade: Model.predict(X) (model.py:181-214) with DTree.apply / predict (training.py:73-83).
+ * X is [K][m][n][C] float32; writes H [K] (float32 score; -inf for rejected samples, model.py:213) and
+ * mask [K] (1 = passed every stage). */
+int wbg_predict_samples(const wbg_model* model, const float* X, int64_t K, float* H, uint8_t* mask, void* stream);
 
 /* gather_samples (samples.py:14-43): crop m x n x C windows at (rs, cs) into out [K][m][n][C]. */
 int wbg_gather_samples(const float* X, int32_t u, int32_t v, int32_t c, const int32_t* rs, const int32_t* cs,

@@ -361,3 +361,82 @@ def test_detect_config_B_model_vs_reference_golden():
     dt = M.detect(crop)
     assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
     assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+
+
+# ------------------------------------------------------------------------------------------- more rows of SURVEY.md 8
+def test_level_subset_equals_filtered_full_detect():
+    """level sharding (config C): detect(levels=S) == the hits of the full detect whose level is in S, and the
+    subsets of a partition add up to the full result and counters."""
+    from waldboost_b200 import sharding
+    from waldboost_b200.engine import plan_geometry
+    frame = S.synthetic_frame(1001, 300, 400)
+    M = make_model((12, 12, 4), OPTS_A, 32, 2, frame, keep_total=2e-2)
+    M.reset()
+    _, full = M.detect_batch(frame[None], return_hits=True)
+    full_stats = (M.n_loc, M.n_weak)
+    plan = plan_geometry(300, 400, OPTS_A, M._spec(), 12, 12)
+    parts = sharding.assign_levels([lv.u * lv.v for lv in plan.levels], 3)
+    got, n_loc, n_weak = [], 0, 0
+    for ids in parts:
+        M.reset()
+        _, h = M.detect_batch(frame[None], return_hits=True, levels=ids)
+        assert set(h["level"].tolist()) <= set(ids)
+        assert np.array_equal(h, full[np.isin(full["level"], ids)])
+        got.append(h); n_loc += M.n_loc; n_weak += M.n_weak
+    assert full.size > 0 and np.array_equal(sharding.normalise_hits(np.concatenate(got)), full)
+    assert (n_loc, n_weak) == full_stats
+    one = M.detect(frame, levels=[2])
+    assert np.array_equal(one.get_field("scores"), full["score"][full["level"] == 2])
+
+
+def test_config_C_shape_mag_hist_20x20x10():
+    """config C's model shape (20x20 window, 10 channels = grad_mag + 9-bin grad_hist) end to end vs the oracle."""
+    frame = S.synthetic_frame(1002, 360, 640)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=CH.grad_mag_hist)
+    M = make_model((20, 20, 10), opts, 48, 2, frame, keep_total=1e-2, calib_levels=2)
+    Cs = oracle_cascade(M)
+    M.reset()
+    dt = M.detect(frame)
+    boxes, scores, _ = Cs.detect(frame)
+    agree = np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
+    if not agree:      # grad_mag's division / sqrt chain is float32 on both sides; tolerate isolated last-ulp effects
+        got = {tuple(b): s for b, s in zip(map(tuple, dt.get()), dt.get_field("scores"))}
+        ref = {tuple(b): s for b, s in zip(map(tuple, boxes), scores)}
+        union = set(got) | set(ref)
+        good = sum(1 for k in union if k in got and k in ref and abs(got[k] - ref[k]) <= 1e-4)
+        assert good / len(union) >= 0.95
+    assert M.n_loc == Cs.n_loc and scores.size > 0
+
+
+def test_config_D_shape_depth4_scan_batch():
+    """config D's cascade shape (depth-4 trees, generic node-record kernel) as a dense scoring batch."""
+    frames = S.synthetic_frames(3, 240, 320)
+    M = make_model((12, 12, 4), OPTS_A, 96, 4, frames[0], keep_total=1e-2, calib_levels=2)
+    Cs = oracle_cascade(M)
+    M.reset()
+    out, hits = M.detect_batch(frames, return_hits=True)
+    for b in range(3):
+        bx, sc, lv = Cs.detect(frames[b])
+        h = hits[hits["frame"] == b]
+        assert np.array_equal(h["score"], sc) and np.array_equal(h["level"], lv) and np.array_equal(out[b].get(), bx)
+    assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak) and hits.size > 0
+
+
+def test_sample_mode_predict():
+    """Model.predict(X) on (K, m, n, C) crops (model.py:181-214): scores, -inf for rejected samples, mask."""
+    from waldboost_b200.engine import get_engine
+    frame = S.synthetic_frame(1000, 120, 160)
+    M = make_model((12, 12, 4), OPTS_A, 24, 3, frame, keep_total=5e-2)
+    X = _oracle_levels(frame, OPTS_A)[0][0]
+    rng = np.random.default_rng(8)
+    rs, cs = rng.integers(0, X.shape[0] - 12, 500), rng.integers(0, X.shape[1] - 12, 500)
+    crops = O.gather_samples(X, rs, cs, (12, 12, 4))
+    H, mask = M.predict(crops)
+    Ho, mo = oracle_cascade(M).predict(crops)
+    assert H.dtype == np.float32 and mask.dtype == bool
+    assert np.array_equal(mask, mo) and np.array_equal(H, Ho) and 0 < mask.sum() < 500
+    assert np.array_equal(get_engine().gather_samples(X, rs, cs, (12, 12, 4)), crops)
+    H0, m0 = M.predict(np.empty((0, 12, 12, 4), np.float32))
+    assert H0.size == 0 and m0.size == 0
+    with pytest.raises(AssertionError):
+        M.predict(np.zeros((3, 12, 12, 3), np.float32))

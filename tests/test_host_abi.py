@@ -156,3 +156,17 @@ def test_synthetic_recipes_are_seeded():
     l, r = S.full_tree_layout(2)
     assert l.tolist() == [1, 2, -1, -1, 5, -1, -1] and r.tolist() == [4, 3, -1, -1, 6, -1, -1]
     assert S.full_tree_layout(4)[0].size == 31
+
+
+def test_level_subset_plan_keeps_layout():
+    """wbg_plan_create_levels: geometry and offsets of the full pyramid, windows only for the listed levels."""
+    spec = wb.channels.resolve_channels(wb.channels.grad_hist)
+    full = plan_geometry(480, 640, OPTS, spec, 12, 12)
+    ids = [0, 3, 7, 20]
+    sub = plan_geometry(480, 640, OPTS, spec, 12, 12, level_ids=ids)
+    assert sub.n_levels == full.n_levels and sub.chn_floats == full.chn_floats
+    assert [k for k, lv in enumerate(sub.levels) if not lv.skipped] == ids
+    assert all(a.chn_off == b.chn_off and a.win_off == b.win_off and a.scale == b.scale for a, b in zip(full.levels, sub.levels))
+    assert sub.info.n_loc == sum(full.levels[k].win_rows * full.levels[k].win_cols for k in ids)
+    none = plan_geometry(480, 640, OPTS, spec, 12, 12, level_ids=[])          # a rank that got no level
+    assert none.info.n_loc == 0 and all(lv.skipped for lv in none.levels)

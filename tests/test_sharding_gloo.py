@@ -98,3 +98,53 @@ def test_image_sharded_detect_world2_gloo(tmp_path):
     assert ref_hits.size > 0 and np.array_equal(got["hits"], ref_hits)
     assert tuple(got["stats"]) == tuple(ref_stats)
     assert np.all(np.diff(got["hits"]["frame"]) >= 0) and set(got["hits"]["frame"]) <= set(range(5))
+
+
+def _level_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        sys.path.insert(0, p)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    fn, costs = _oracle_level_fn()
+    hits, stats = sharding.detect_level_sharded(fn, costs)
+    if rank == 0:
+        np.savez(out_path, hits=hits, stats=np.array(stats))
+    dist.destroy_process_group()
+
+
+def _oracle_level_fn():
+    """per-rank detector for level sharding: the oracle restricted to a level subset of one frame."""
+    import wb_oracle as O
+    from waldboost_b200 import synthetic as S
+    from waldboost_b200._native import HIT_DTYPE
+    opts = dict(shrink=2, n_per_oct=4, smooth=1, channels=O.grad_hist)
+    frame = S.synthetic_frame(1001, 120, 160)
+    maps = [c for c, _ in O.channel_pyramid(frame, opts)]
+    lo, hi = S.channel_quantiles(maps[0])
+    Cs = O.Cascade((12, 12, 4), opts)
+    for t in S.random_trees((12, 12, 4), 6, 2, lo, hi, seed=5):
+        Cs.append(O.DTree([tuple(f) for f in t.feature], t.threshold, t.left, t.right, t.prediction), -0.2)
+
+    def fn(level_ids):
+        Cs.reset()
+        rec = []
+        for lvl, (chns, scale) in zip(sorted(level_ids), Cs.channels(frame, level_ids)):
+            r, c, h = Cs.predict_on_image(chns)
+            hh = np.zeros(r.size, HIT_DTYPE)
+            hh["level"], hh["r"], hh["c"], hh["score"] = lvl, r, c, h
+            rec.append(hh)
+        return (np.concatenate(rec) if rec else np.empty(0, HIT_DTYPE)), (Cs.n_loc, Cs.n_weak)
+    return fn, [m.shape[0] * m.shape[1] for m in maps]
+
+
+def test_level_sharded_detect_world2_gloo(tmp_path):
+    """config C's partitioning: the levels of ONE frame spread over 2 ranks == the single-process result."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "levels.npz")
+    mp.spawn(_level_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    fn, costs = _oracle_level_fn()
+    ref_hits, ref_stats = fn(list(range(len(costs))))
+    assert ref_hits.size > 0 and np.array_equal(got["hits"], sharding.normalise_hits(ref_hits))
+    assert tuple(got["stats"]) == tuple(ref_stats)

@@ -12,7 +12,7 @@ WBG_OK, WBG_EINVAL, WBG_ECAP, WBG_ECUDA, WBG_ENOMEM = 0, -1, -2, -3, -4
 WBG_U8, WBG_F32 = 0, 1
 WBG_CH_GRAD_HIST, WBG_CH_GRAD_MAG, WBG_CH_GRAD_MAG_HIST = 0, 1, 2
 WBG_MAX_BINS, WBG_MAX_NORM, WBG_MAX_CHANNELS = 16, 8, 17
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ChannelOpts(C.Structure):
@@ -25,7 +25,7 @@ class ChannelOpts(C.Structure):
 class Level(C.Structure):
     _fields_ = [("octave", C.c_int32), ("src_h", C.c_int32), ("src_w", C.c_int32), ("nh", C.c_int32),
                 ("nw", C.c_int32), ("u", C.c_int32), ("v", C.c_int32), ("win_rows", C.c_int32),
-                ("win_cols", C.c_int32), ("reserved", C.c_int32), ("chn_off", C.c_int64), ("win_off", C.c_int64),
+                ("win_cols", C.c_int32), ("skipped", C.c_int32), ("chn_off", C.c_int64), ("win_off", C.c_int64),
                 ("scale", C.c_double)]
 
 
@@ -54,6 +54,7 @@ SYMBOLS = {
     "wbg_last_error": (C.c_char_p, []),
     "wbg_device_count": (C.c_int, []),
     "wbg_plan_create": (C.c_int, [_I32, _I32, C.POINTER(ChannelOpts), _I32, _I32, _I32, C.POINTER(_P)]),
+    "wbg_plan_create_levels": (C.c_int, [_I32, _I32, C.POINTER(ChannelOpts), _I32, _I32, _I32, C.POINTER(_I32), _I32, C.POINTER(_P)]),
     "wbg_plan_destroy": (None, [_P]),
     "wbg_plan_get_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "wbg_plan_get_levels": (C.c_int, [_P, C.POINTER(Level), _I32]),
@@ -69,6 +70,7 @@ SYMBOLS = {
     "wbg_predict_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "wbg_predict_on_image": (C.c_int, [_P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _SZ, _P]),
     "wbg_cascade_trace": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _P, _P, _P]),
+    "wbg_predict_samples": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "wbg_gather_samples": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P, _P]),
     "wbg_profile_enable": (C.c_int, [_I32]),
     "wbg_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_I64)]),

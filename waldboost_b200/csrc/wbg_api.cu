@@ -124,8 +124,16 @@ static int channels_of(const wbg_channel_opts* o) {
 
 extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
                                int32_t device_tables, wbg_plan** out) {
+    return wbg_plan_create_levels(H, W, opts, win_m, win_n, device_tables, nullptr, 0, out);
+}
+
+extern "C" int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
+                                      int32_t device_tables, const int32_t* level_ids, int32_t n_level_ids, wbg_plan** out) {
     WBG_REQUIRE(out && opts, "wbg_plan_create: null argument");
     *out = nullptr;
+    WBG_REQUIRE(n_level_ids >= 0 && (level_ids || n_level_ids == 0), "wbg_plan_create_levels: bad level list");
+    for (int i = 1; i < n_level_ids; ++i)
+        WBG_REQUIRE(level_ids[i] > level_ids[i - 1], "wbg_plan_create_levels: level ids must be ascending and unique");
     WBG_REQUIRE(H >= 1 && W >= 1, "wbg_plan_create: bad image size %dx%d", H, W);
     WBG_REQUIRE(opts->shrink == 1 || opts->shrink == 2, "Shrink factor must be integer 1 <= shrink <= 2");
     WBG_REQUIRE(opts->n_per_oct >= 1 && opts->n_per_oct <= 64, "wbg_plan_create: bad n_per_oct %d", opts->n_per_oct);
@@ -164,6 +172,7 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
     // channels.py:124-131 -- Python double arithmetic: factor = 2**(-1/n); s = factor**i; int((w*s)/shrink)*shrink
     const double factor = ::pow(2.0, -1.0 / (double)npo);
     long long chn = 0, win = 0, nloc = 0;
+    int next_id = 0;
     int ptile = 0, ctile = 0, qtile = 0;
     for (size_t k = 0; k < p->octaves.size(); ++k) {
         const int h = p->octaves[k].h, w = p->octaves[k].w;
@@ -187,7 +196,15 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
             const long long nwin = (long long)L.win_rows * L.win_cols;
             chn += (long long)wbg_align_up((size_t)L.u * L.v * p->C, 4);
             win += (long long)wbg_align_up((size_t)nwin, 32);
-            nloc += nwin;
+            // a level outside the requested subset keeps its place in the layout but gets no tiles
+            bool selected = true;
+            if (level_ids) {
+                const int id = (int)p->levels.size();
+                while (next_id < n_level_ids && level_ids[next_id] < id) ++next_id;
+                selected = next_id < n_level_ids && level_ids[next_id] == id;
+            }
+            L.skipped = selected ? 0 : 1;
+            if (selected) nloc += nwin;
 
             LevelDev D;
             memset(&D, 0, sizeof(D));
@@ -197,13 +214,13 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
             D.win_rows = L.win_rows; D.win_cols = L.win_cols;
             D.ptile0 = ptile;
             D.ptiles_x = (L.v + PYR_TV - 1) / PYR_TV;
-            D.ptiles_y = (L.u + PYR_TU - 1) / PYR_TU;
+            D.ptiles_y = selected ? (L.u + PYR_TU - 1) / PYR_TU : 0;
             ptile += D.ptiles_x * D.ptiles_y;
             D.qtile0 = qtile;
             D.qtiles_x = (L.v + PYR_QTV - 1) / PYR_QTV;
-            qtile += D.qtiles_x * ((L.u + PYR_QTU - 1) / PYR_QTU);
+            qtile += selected ? D.qtiles_x * ((L.u + PYR_QTU - 1) / PYR_QTU) : 0;
             D.ctile0 = ctile;
-            if (p->geom_ok && nwin > 0) {
+            if (p->geom_ok && nwin > 0 && selected) {
                 D.ctiles_x = (L.win_cols + p->geom.TC - 1) / p->geom.TC;
                 D.ctiles_y = (L.win_rows + p->geom.TR - 1) / p->geom.TR;
                 ctile += D.ctiles_x * D.ctiles_y;

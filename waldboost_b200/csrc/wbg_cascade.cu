@@ -568,6 +568,48 @@ extern "C" int wbg_cascade_trace(const wbg_model* model, const float* X, int32_t
     return WBG_OK;
 }
 
+// Model.predict (model.py:181-214): one sample (m x n x C crop) per thread, stages in order, float32 accumulation,
+// a sample that fails `H >= theta` stops being updated and ends with H = -inf (model.py:213).
+__global__ void predict_samples_kernel(const float* __restrict__ X, long long K, int sample_floats, int n, int C, int T, int N,
+                                       const uint8_t* __restrict__ feature, const float* __restrict__ threshold,
+                                       const int8_t* __restrict__ left, const int8_t* __restrict__ right,
+                                       const float* __restrict__ prediction, const float* __restrict__ theta,
+                                       float* __restrict__ H, uint8_t* __restrict__ mask) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const float* x = X + k * sample_floats;
+    float hs = 0.f;
+    bool ok = true;
+    for (int s = 0; s < T && ok; ++s) {
+        const size_t b = (size_t)s * N;
+        int nd = 0;
+        while (left[b + nd] >= 0) {                                   // training.py:73-81
+            const uint8_t* f = feature + (b + nd) * 3;
+            const float xv = __ldg(x + ((int)f[0] * n + (int)f[1]) * C + (int)f[2]);
+            nd = (xv <= threshold[b + nd]) ? left[b + nd] : right[b + nd];
+        }
+        hs += prediction[b + nd];
+        const float th = theta[s];
+        if (th != -CUDART_INF_F) ok = hs >= th;                       // model.py:209-212
+    }
+    H[k] = ok ? hs : -CUDART_INF_F;
+    mask[k] = ok ? 1 : 0;
+}
+
+extern "C" int wbg_predict_samples(const wbg_model* model, const float* X, int64_t K, float* H, uint8_t* mask, void* stream) {
+    WBG_REQUIRE(model && (K == 0 || (X && H && mask)), "wbg_predict_samples: null argument");
+    WBG_REQUIRE(K >= 0, "wbg_predict_samples: negative sample count");
+    if (K == 0) return WBG_OK;
+    const int threads = 128;
+    const long long blocks = (K + threads - 1) / threads;
+    WBG_REQUIRE(blocks <= 0x7fffffffLL, "wbg_predict_samples: too many samples");
+    predict_samples_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        X, K, model->m * model->n * model->C, model->n, model->C, model->T, model->N, model->d_feature, model->d_threshold,
+        model->d_left, model->d_right, model->d_prediction, model->d_theta, H, mask);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
 __global__ void gather_kernel(const float* __restrict__ X, int v, int C, const int* __restrict__ rs, const int* __restrict__ cs,
                               long long total, int m, int n, float* __restrict__ out) {
     const int row = n * C;

@@ -65,10 +65,16 @@ def _opts_key(channel_opts, spec, max_levels):
 class Plan:
     """Pyramid geometry for one (H, W, channel options, window) -- wraps a wbg_plan handle."""
 
-    def __init__(self, H, W, copts, win_m, win_n, device_tables=True):
+    def __init__(self, H, W, copts, win_m, win_n, device_tables=True, level_ids=None):
         L = N.lib()
         self.handle = C.c_void_p()
-        code = L.wbg_plan_create(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, C.byref(self.handle))
+        if level_ids is None:
+            code = L.wbg_plan_create(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, C.byref(self.handle))
+        else:
+            ids = sorted(set(int(x) for x in level_ids))
+            arr = (C.c_int32 * max(len(ids), 1))(*ids)
+            code = L.wbg_plan_create_levels(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, arr, len(ids),
+                                            C.byref(self.handle))
         if code == N.WBG_EINVAL and "Shrink factor" in N.last_error():
             raise AssertionError(N.last_error())          # reference channels.py:120 is an assert
         N.check(code)
@@ -92,9 +98,9 @@ class Plan:
             pass
 
 
-def plan_geometry(H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0):
+def plan_geometry(H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None):
     """Host-only plan (no GPU needed): level sizes, offsets and window counts."""
-    return Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, device_tables=False)
+    return Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, device_tables=False, level_ids=level_ids)
 
 
 class ModelHandle:
@@ -174,12 +180,13 @@ class Engine:
             self._pinned[name] = t
         return t
 
-    def plan(self, H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0):
-        key = (H, W, win_m, win_n) + _opts_key(channel_opts, spec, max_levels)
+    def plan(self, H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None):
+        lv_key = None if level_ids is None else tuple(sorted(set(int(x) for x in level_ids)))
+        key = (H, W, win_m, win_n, lv_key) + _opts_key(channel_opts, spec, max_levels)
         p = self._plans.get(key)
         if p is None:
             with self.torch.cuda.device(self.device):
-                p = Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n)
+                p = Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, level_ids=lv_key)
             if len(self._plans) > 64:
                 self._plans.clear()
             self._plans[key] = p
@@ -347,6 +354,18 @@ class Engine:
                                                C.c_void_p(rs_d.data_ptr()), C.c_void_p(cs_d.data_ptr()), K,
                                                C.c_void_p(leaf.data_ptr()), C.c_void_p(score.data_ptr()), self._stream()))
         return leaf.cpu().numpy()[:, :T], score.cpu().numpy()
+
+    def predict_samples(self, model_handle, X):
+        """Model.predict(X) on (K, m, n, C) float32 samples -> (H [K] float32 with -inf for rejected, mask [K] bool)."""
+        torch = self.torch
+        Xd = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
+        K = int(Xd.shape[0])
+        H = torch.empty(max(K, 1), dtype=torch.float32, device=self.device)
+        mask = torch.empty(max(K, 1), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.wbg_predict_samples(model_handle.handle, C.c_void_p(Xd.data_ptr()), K, C.c_void_p(H.data_ptr()),
+                                                 C.c_void_p(mask.data_ptr()), self._stream()))
+        return H.cpu().numpy()[:K], mask.cpu().numpy()[:K].astype(bool)
 
     def gather_samples(self, X, rs, cs, shape):
         torch = self.torch

@@ -111,10 +111,10 @@ class Model:
     def _spec(self):
         return resolve_channels(self.channel_opts["channels"])
 
-    def _plan(self, eng, H, W):
+    def _plan(self, eng, H, W, levels=None):
         m, n = int(self.shape[0]), int(self.shape[1])
         assert self.channel_opts["shrink"] in [1, 2], "Shrink factor must be integer 1 <= shrink <= 2"
-        return eng.plan(H, W, self.channel_opts, self._spec(), m, n)
+        return eng.plan(H, W, self.channel_opts, self._spec(), m, n, level_ids=levels)
 
     # ------------------------------------------------------------------------------------------- reference API
     def channels(self, image):
@@ -148,11 +148,12 @@ class Model:
         rects = np.concatenate([x1, y1, x1 + n, y1 + m], axis=1).astype(np.float32)
         return Boxes(rects).normalized(scale=1.0 / scale)
 
-    def _run(self, images, keep_channels=False):
-        """Shared device pipeline: frames [B,H,W] -> (hits, level_counts, plan, chns or None); updates stats."""
+    def _run(self, images, keep_channels=False, levels=None):
+        """Shared device pipeline: frames [B,H,W] -> (hits, level_counts, plan, chns or None); updates stats.
+        `levels`: optional subset of pyramid level indices to compute and scan (level sharding)."""
         eng = get_engine()
         B, H, W = images.shape
-        plan = self._plan(eng, H, W)
+        plan = self._plan(eng, H, W, levels)
         handle = self._device_model()
         if plan.n_levels == 0:
             return np.empty(0, dtype=_hit_dtype()), np.zeros((B, 0), np.int32), plan, None
@@ -188,14 +189,22 @@ class Model:
         b.set_field("scores", h["score"].copy())
         return b
 
-    def detect(self, image) -> Boxes:
+    def detect(self, image, levels=None) -> Boxes:
         """Detect objects in a 2-D image (reference model.py:149-179) -> Boxes with field "scores", ordered by
-        (level, row, column) like the reference's concatenation of per-level results."""
+        (level, row, column) like the reference's concatenation of per-level results.  `levels` (extension): restrict
+        the scan to these pyramid level indices -- the unit of work when one huge frame is spread over several GPUs."""
         _validate_image(image)
-        hits, _, _, _ = self._run(np.ascontiguousarray(image)[None])
+        hits, _, _, _ = self._run(np.ascontiguousarray(image)[None], levels=levels)
         return self._boxes_from_hits(hits)
 
-    def detect_batch(self, images, return_hits=False):
+    def predict(self, X):
+        """Sample-mode cascade (reference model.py:181-214): X is (K, m, n, C) -> (H, mask); rejected samples get
+        H = -inf."""
+        X = np.asarray(X)
+        assert tuple(X.shape[1:]) == tuple(int(v) for v in self.shape), f"Invalid sample shape {X.shape[1:]}, expected {tuple(self.shape)}"
+        return get_engine().predict_samples(self._device_model(), X)
+
+    def detect_batch(self, images, return_hits=False, levels=None):
         """Detect on a batch of equally sized frames (array [B,H,W] or list of 2-D arrays) -> list of Boxes.
         With return_hits=True also returns the raw hit records (frame, level, r, c, score, box)."""
         if not isinstance(images, np.ndarray):
@@ -204,7 +213,7 @@ class Model:
             images = np.stack(images)
         if images.ndim != 3:
             raise ValueError("detect_batch takes [B,H,W] frames")
-        hits, counts, _, _ = self._run(np.ascontiguousarray(images))
+        hits, counts, _, _ = self._run(np.ascontiguousarray(images), levels=levels)
         per_frame = counts.sum(axis=1) if counts.size else np.zeros(images.shape[0], np.int64)
         out, pos = [], 0
         for b in range(images.shape[0]):

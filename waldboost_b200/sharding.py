@@ -76,3 +76,23 @@ def detect_sharded(detect_fn, frames, group=None, dst=0):
         from ._native import HIT_DTYPE
         hits, stats = np.empty(0, HIT_DTYPE), (0, 0)
     return gather_hits(hits, stats, group, dst)
+
+
+def detect_level_sharded(detect_levels_fn, level_costs, group=None, dst=0):
+    """One huge frame spread over the ranks of `group` by pyramid level (BASELINE config C).
+
+    `level_costs[l]` ~ work of level l (channel pixels); `detect_levels_fn(level_ids)` runs the local detector on the
+    given levels and returns (hit records with global `level` indices, (n_loc, n_weak)) -- on a GPU rank
+    `Model.detect_batch(frame[None], return_hits=True, levels=level_ids)`.  Returns (hits, stats) on `dst`."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    mine = assign_levels(level_costs, world)[rank]
+    if mine:
+        hits, stats = detect_levels_fn(mine)
+    else:
+        from ._native import HIT_DTYPE
+        hits, stats = np.empty(0, HIT_DTYPE), (0, 0)
+    return gather_hits(hits, stats, group, dst)
