@@ -33,6 +33,11 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libwbg cannot be built (there is no CPU fallback)")
 
 
+def _extra_defs():
+    """tuning aid: extra nvcc flags (e.g. -DH4_MINB=6) from the environment"""
+    return os.environ.get("WBG_NVCC_DEFS", "").split()
+
+
 def _digest():
     h = hashlib.sha256()
     files = sorted(os.listdir(CSRC)) + ["../../include/wbg.h"]
@@ -42,7 +47,7 @@ def _digest():
             h.update(f.encode())
             with open(p, "rb") as fh:
                 h.update(fh.read())
-    h.update(repr((ARCH, COMMON[:4], SOURCES)).encode())
+    h.update(repr((ARCH, COMMON[:4], SOURCES, _extra_defs())).encode())
     return h.hexdigest()
 
 
@@ -56,7 +61,7 @@ def build(force=False, verbose=False):
     objs = []
     for src, extra in SOURCES.items():
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + extra + _extra_defs() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

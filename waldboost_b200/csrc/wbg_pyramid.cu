@@ -578,7 +578,10 @@ __device__ __noinline__ float hist4_exact_bin2(const float* __restrict__ s_R, in
     return (float)(a / 16.0);
 }
 
-__global__ void __launch_bounds__(H4_THREADS) level_hist4_u8_kernel(const PyrParams p) {
+#ifndef H4_MINB
+#define H4_MINB 6
+#endif
+__global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(const PyrParams p) {
     constexpr int PH = H4_PH, PW = H4_PW, RH = H4_RH, RW = H4_RW;
     __shared__ __align__(16) TapF s_tapr[RH];
     __shared__ __align__(16) TapF s_tapc[RW];
@@ -830,6 +833,7 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
             const long long grid_q = (long long)plan->qtiles * batch;
             WBG_REQUIRE(grid_q <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid_q);
             p.tiles_per_frame = plan->qtiles;
+            WBG_CUDA_TRY(cudaFuncSetAttribute(level_hist4_u8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);
             level_hist4_u8_kernel<<<(unsigned)grid_q, H4_THREADS, 0, stream>>>(p);
             wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);

@@ -201,7 +201,7 @@ class Engine:
             return N.WBG_F32
         raise TypeError(f"image dtype {dtype} is not supported on the GPU path (uint8 and float32 only; no CPU fallback)")
 
-    def upload_images(self, images):
+    def upload_images(self, images, slot=""):
         """numpy [B,H,W] (uint8 / float32) -> device tensor.  Page-locked input (e.g. a NumPy view of a pinned torch
         tensor) is copied straight to the device; pageable input goes through a cached pinned staging buffer."""
         torch = self.torch
@@ -209,27 +209,27 @@ class Engine:
         self.image_dtype(images.dtype)
         nbytes = images.nbytes
         tdt = torch.uint8 if images.dtype == np.uint8 else torch.float32
-        dev = self.buffer("img", nbytes)[:nbytes].view(tdt).view(images.shape)
+        dev = self.buffer("img" + slot, nbytes)[:nbytes].view(tdt).view(images.shape)
         src = torch.from_numpy(images) if images.flags.writeable else None
         if src is not None and src.is_pinned():
             dev.copy_(src, non_blocking=True)
             return dev
-        stage = self.pinned("img", nbytes)
+        stage = self.pinned("img" + slot, nbytes)
         stage_np = stage.numpy()[:nbytes].view(images.dtype).reshape(images.shape)
         np.copyto(stage_np, images)
         dev.copy_(stage[:nbytes].view(tdt).view(images.shape), non_blocking=True)
         return dev
 
-    def pyramid(self, img_dev, plan, out=None):
+    def pyramid(self, img_dev, plan, out=None, slot=""):
         """img_dev: device tensor [B,H,W] uint8/float32 -> chns device tensor [B, chn_floats] float32."""
         torch = self.torch
         B = int(img_dev.shape[0])
         dt = N.WBG_U8 if img_dev.dtype == torch.uint8 else N.WBG_F32
         assert img_dev.is_contiguous() and img_dev.shape[1] == plan.info.H and img_dev.shape[2] == plan.info.W
         if out is None:
-            out = self.buffer("chns", 4 * B * max(plan.chn_floats, 1))[:4 * B * plan.chn_floats].view(torch.float32).view(B, plan.chn_floats)
+            out = self.buffer("chns" + slot, 4 * B * max(plan.chn_floats, 1))[:4 * B * plan.chn_floats].view(torch.float32).view(B, plan.chn_floats)
         wsb = self.lib.wbg_pyramid_workspace_bytes(plan.handle, dt, B)
-        ws = self.buffer("pyr_ws", wsb)
+        ws = self.buffer("pyr_ws" + slot, wsb)
         with torch.cuda.device(self.device):
             N.check(self.lib.wbg_channel_pyramid(plan.handle, C.c_void_p(img_dev.data_ptr()), dt, B,
                                                  C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
@@ -257,10 +257,10 @@ class Engine:
         return [(lv.copy(), s) for lv, s in zip(self.split_levels(host, plan), plan.scales)]
 
     # ------------------------------------------------------------------------------------------- cascade
-    def _meta(self, B, n_levels):
+    def _meta(self, B, n_levels, slot=""):
         """one device buffer holding [n_hits i64][stats u64 x 2B][level_counts i32 x B*L] -> sub-pointers."""
         nbytes = 8 + 16 * B + 4 * B * n_levels
-        t = self.buffer("meta", nbytes)
+        t = self.buffer("meta" + slot, nbytes)
         base = t.data_ptr()
         return t, nbytes, base, base + 8, base + 8 + 16 * B
 
@@ -283,13 +283,13 @@ class Engine:
         self.torch.cuda.current_stream(self.device).synchronize()
         return host.numpy()[:nb].view(N.HIT_DTYPE).copy()
 
-    def cascade_launch(self, model_handle, plan, chns, B, hit_cap):
+    def cascade_launch(self, model_handle, plan, chns, B, hit_cap, slot=""):
         """Enqueue the cascade over every level of B frames on the current stream (no synchronisation).
         Returns (hits device buffer, meta device buffer, meta bytes)."""
         lib = self.lib
-        ws = self.buffer("cas_ws", lib.wbg_cascade_workspace_bytes(plan.handle, B))
-        hits_t = self.buffer("hits", hit_cap * N.HIT_DTYPE.itemsize)
-        meta, nbytes, p_nhits, p_stats, p_counts = self._meta(B, plan.n_levels)
+        ws = self.buffer("cas_ws" + slot, lib.wbg_cascade_workspace_bytes(plan.handle, B))
+        hits_t = self.buffer("hits" + slot, hit_cap * N.HIT_DTYPE.itemsize)
+        meta, nbytes, p_nhits, p_stats, p_counts = self._meta(B, plan.n_levels, slot)
         with self.torch.cuda.device(self.device):
             code = lib.wbg_cascade_scan(model_handle.handle, plan.handle, C.c_void_p(chns.data_ptr()), B,
                                         C.c_void_p(hits_t.data_ptr()), hit_cap, C.c_void_p(p_counts),
@@ -313,6 +313,77 @@ class Engine:
             if n_hits <= hit_cap:
                 return self._read_hits(hits_t, n_hits), counts, stats
             hit_cap = n_hits  # WBG_ECAP semantics: only the first hit_cap were stored -> re-run with room for all
+
+    def run_frames(self, model_handle, plan, images, chunk=16):
+        """detect() over host frames [B,H,W] as a two-slot pipeline: the frames go to the device in chunks, and the
+        host->device copy of chunk k+1 (copy engine) overlaps the pyramid + cascade kernels of chunk k (two streams,
+        one buffer set each).  Returns (hits with batch-global frame indices, level_counts [B,L], stats [B,2])."""
+        torch = self.torch
+        B = int(images.shape[0])
+        if B <= chunk:
+            dev = self.upload_images(images)
+            chns = self.pyramid(dev, plan)
+            return self.cascade(model_handle, plan, chns, B)
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
+        jobs = []
+        for i, (lo, hi) in enumerate(spans):
+            slot = str(i & 1)
+            st = self._pipe_streams[i & 1]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                n = hi - lo
+                dev = self.upload_images(images[lo:hi], slot)
+                chns = self.pyramid(dev, plan, slot=slot)
+                cap = self.default_hit_cap(plan, n)
+                hits_t, meta, nbytes = self.cascade_launch(model_handle, plan, chns, n, cap, slot)
+                host_meta = self.pinned("meta%d" % i, nbytes)
+                host_meta[:nbytes].copy_(meta[:nbytes], non_blocking=True)
+                # the hit list is small in practice: copy an optimistic prefix right away, the rest on demand
+                pre = min(cap, 4096) * N.HIT_DTYPE.itemsize
+                host_hits = self.pinned("hits%d" % i, pre)
+                host_hits[:pre].copy_(hits_t[:pre], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            jobs.append([lo, hi, slot, st, ev, host_meta, nbytes, host_hits, pre, cap])
+            if i >= 1:
+                # slot buffers are reused two chunks later: finish reading chunk i-1 before chunk i+1 overwrites them
+                self._collect(jobs[i - 1], model_handle, plan, images)
+        self._collect(jobs[-1], model_handle, plan, images)
+        cur.wait_stream(self._pipe_streams[0])
+        cur.wait_stream(self._pipe_streams[1])
+        hits = np.concatenate([j[-1][0] for j in jobs]) if jobs else np.empty(0, N.HIT_DTYPE)
+        counts = np.concatenate([j[-1][1] for j in jobs], axis=0)
+        stats = np.concatenate([j[-1][2] for j in jobs], axis=0)
+        return hits, counts, stats
+
+    def _collect(self, job, model_handle, plan, images):
+        """wait for one pipeline chunk and read its results back (appends the result tuple to the job record)."""
+        lo, hi, slot, st, ev, host_meta, nbytes, host_hits, pre, cap = job[:10]
+        if len(job) > 10:
+            return
+        n = hi - lo
+        ev.synchronize()
+        raw = host_meta.numpy()[:nbytes]
+        n_hits = int(raw[:8].view(np.int64)[0])
+        stats = raw[8:8 + 16 * n].view(np.uint64).reshape(n, 2).copy()
+        counts = raw[8 + 16 * n:nbytes].view(np.int32).reshape(n, plan.n_levels).copy()
+        nb = n_hits * N.HIT_DTYPE.itemsize
+        if n_hits > cap:
+            # more survivors than the buffer holds: redo this chunk on its stream with room for all of them
+            with self.torch.cuda.stream(st):
+                dev = self.upload_images(images[lo:hi], slot)
+                chns = self.pyramid(dev, plan, slot=slot)
+                hits, counts, stats = self.cascade(model_handle, plan, chns, n, hit_cap=n_hits)
+        elif nb <= pre:
+            hits = host_hits.numpy()[:nb].view(N.HIT_DTYPE).copy()
+        else:
+            with self.torch.cuda.stream(st):
+                hits = self._read_hits(self._bufs["hits" + slot], n_hits)
+        hits["frame"] += lo
+        job.append((hits, counts, stats))
 
     def predict_on_map(self, model_handle, X, hit_cap=None):
         """Model.predict_on_image on one channel map X (numpy or device tensor, (u,v,C) float32)."""

@@ -157,12 +157,16 @@ class Model:
         handle = self._device_model()
         if plan.n_levels == 0:
             return np.empty(0, dtype=_hit_dtype()), np.zeros((B, 0), np.int32), plan, None
-        dev = eng.upload_images(images)
-        chns = eng.pyramid(dev, plan)
-        hits, counts, stats = eng.cascade(handle, plan, chns, B)
+        if keep_channels:
+            dev = eng.upload_images(images)
+            chns = eng.pyramid(dev, plan)
+            hits, counts, stats = eng.cascade(handle, plan, chns, B)
+        else:
+            chns = None
+            hits, counts, stats = eng.run_frames(handle, plan, images)
         self.n_loc += int(stats[:, 0].sum())
         self.n_weak += int(stats[:, 1].sum())
-        return hits, counts, plan, (chns if keep_channels else None)
+        return hits, counts, plan, chns
 
     def scan_channels(self, image):
         """Generator of (chns, scale, (r, c, h)) per level (reference model.py:105-134)."""
