@@ -89,6 +89,8 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
+    int cnum = env_int("WBG_CAS_COMPACT_NUM", 1), cden = env_int("WBG_CAS_COMPACT_DEN", 2);
+    if (cnum < 1 || cden <= cnum) { cnum = 1; cden = 2; }
     int idx = 0;
     for (auto& c : cand) {
         if (idx++ < skip) continue;
@@ -96,14 +98,14 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
         int pitch = c.TC + n - 1;
         pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are re-packed
         const long long plane = (long long)rows * pitch;
-        const int list_cap = c.threads * c.wpt / 2;
+        // the re-pack lists hold at most the survivors of a re-pack: slots * num / den
+        const int list_cap = (int)(((long long)c.threads * c.wpt * cnum + cden - 1) / cden);
         const long long bytes = plane * C * 4 + (long long)list_cap * (4 + 2) + 256;
         if (bytes <= c.budget && plane < 65536) {
             g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
             g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap;
-            g->compact_num = env_int("WBG_CAS_COMPACT_NUM", 1);
-            g->compact_den = env_int("WBG_CAS_COMPACT_DEN", 2);
-            if (g->compact_num < 1 || g->compact_den < 2 * g->compact_num) { g->compact_num = 1; g->compact_den = 2; }
+            g->compact_num = cnum;
+            g->compact_den = cden;
             g->round_full = env_int("WBG_CAS_ROUND_FULL", 16);
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 32);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 64);

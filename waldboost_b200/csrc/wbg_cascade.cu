@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kerne
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const int idx = tid + k * stride;
-            const bool has = k < 4 && tid < stride && idx < n_slots;
+            const bool has = (k < 4 || stride == THREADS) && tid < stride && idx < n_slots;
             wa[k] = tile_base + 4u * (has ? (unsigned)s_woff[idx] : 0u);
             hs[k] = has ? s_score[idx] : CUDART_NAN_F;
         }

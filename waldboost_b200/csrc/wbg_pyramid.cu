@@ -92,6 +92,40 @@ __global__ void __launch_bounds__(256) octave_kernel(const T* __restrict__ src, 
     block_minmax_commit(mn, mx, mm + (long long)blockIdx.y * n_oct + oct);
 }
 
+// uint8 octave step with 8-byte loads: each thread produces 4 adjacent output pixels from two 8-byte source segments
+// (channels.py:55-64: widened sum, true division, truncation) and, when SRC_MM, also folds the SOURCE pixels into the
+// min/max of octave `oct - 1` (all of them are read when the source has even height and width).
+// Requires sw % 8 == 0, dw % 4 == 0 and 8-byte aligned frame bases.
+template <bool SRC_MM>
+__global__ void __launch_bounds__(256) octave_u8_vec_kernel(const uint8_t* __restrict__ src, long long src_stride, int sw,
+                                                            uint8_t* __restrict__ dst, long long dst_stride, int dh, int dw,
+                                                            int2* mm, int n_oct, int oct) {
+    const uint8_t* s = src + (long long)blockIdx.y * src_stride;
+    uint8_t* d = dst + (long long)blockIdx.y * dst_stride;
+    const int qw = dw >> 2, total = dh * qw;
+    int mn = 255, mx = 0, smn = 255, smx = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / qw, q = i - y * qw;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(s + (long long)(2 * y) * sw + 8 * q));
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(s + (long long)(2 * y + 1) * sw + 8 * q));
+        // per 16-bit lane: byte pair sums of both rows; the pooled pixel is (a0 + a1 + b0 + b1) >> 2
+        const unsigned a_lo = (a.x & 0x00ff00ffu) + ((a.x >> 8) & 0x00ff00ffu), a_hi = (a.y & 0x00ff00ffu) + ((a.y >> 8) & 0x00ff00ffu);
+        const unsigned b_lo = (b.x & 0x00ff00ffu) + ((b.x >> 8) & 0x00ff00ffu), b_hi = (b.y & 0x00ff00ffu) + ((b.y >> 8) & 0x00ff00ffu);
+        const unsigned lo = ((a_lo + b_lo) >> 2) & 0x00ff00ffu, hi = ((a_hi + b_hi) >> 2) & 0x00ff00ffu;   // sums < 1024 per lane
+        const unsigned o0 = lo & 0xffu, o1 = lo >> 16, o2 = hi & 0xffu, o3 = hi >> 16;
+        *reinterpret_cast<unsigned*>(d + (long long)y * dw + 4 * q) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        mn = min(min(mn, (int)min(o0, o1)), (int)min(o2, o3));
+        mx = max(max(mx, (int)max(o0, o1)), (int)max(o2, o3));
+        if (SRC_MM) {
+            const unsigned v0 = __vminu4(__vminu4(a.x, a.y), __vminu4(b.x, b.y)), v1 = __vmaxu4(__vmaxu4(a.x, a.y), __vmaxu4(b.x, b.y));
+            smn = min(smn, (int)min(min(v0 & 0xffu, (v0 >> 8) & 0xffu), min((v0 >> 16) & 0xffu, v0 >> 24)));
+            smx = max(smx, (int)max(max(v1 & 0xffu, (v1 >> 8) & 0xffu), max((v1 >> 16) & 0xffu, v1 >> 24)));
+        }
+    }
+    block_minmax_commit(mn, mx, mm + (long long)blockIdx.y * n_oct + oct);
+    if (SRC_MM) block_minmax_commit(smn, smx, mm + (long long)blockIdx.y * n_oct + oct - 1);
+}
+
 // ------------------------------------------------------------------------------------------------ level kernel
 struct PyrParams {
     const void* img;
@@ -788,7 +822,15 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
     const int n_mm = batch * n_oct;
     minmax_init_kernel<<<(n_mm + 255) / 256, 256, 0, stream>>>(mm, n_mm);
     WBG_CUDA_TRY(cudaGetLastError());
-    {
+    // uint8 fast path: 8-byte loads, and the min/max of the frame itself folded into the first octave step (possible
+    // when the 2x2 pooling reads every source pixel, i.e. even height and width)
+    auto vec_ok = [&](const OctaveInfo& a, const OctaveInfo& b, const void* sp, long long sstride) {
+        return sizeof(T) == 1 && a.w % 8 == 0 && b.w % 4 == 0 && b.w >= 4 && sstride % 8 == 0 &&
+               (reinterpret_cast<uintptr_t>(sp) & 7u) == 0;
+    };
+    const bool fuse_mm = n_oct > 1 && vec_ok(plan->octaves[0], plan->octaves[1], img, img_stride) &&
+                         plan->octaves[0].h % 2 == 0 && plan->octaves[0].w % 2 == 0;
+    if (!fuse_mm) {
         int bx = (int)((img_stride + 256 * 16 - 1) / (256 * 16));
         if (bx > 1024) bx = 1024;
         if (bx < 1) bx = 1;
@@ -800,9 +842,20 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
         const OctaveInfo& b = plan->octaves[k];
         const T* src = k == 1 ? img : oct_ws + a.off;
         const long long src_stride = k == 1 ? img_stride : oct_stride;
-        int bx = (b.h * b.w + 255) / 256;
-        if (bx > 2048) bx = 2048;
-        octave_kernel<T><<<dim3(bx, batch), 256, 0, stream>>>(src, src_stride, a.w, oct_ws + b.off, oct_stride, b.h, b.w, mm, n_oct, k);
+        if (vec_ok(a, b, src, src_stride)) {
+            int bx = (b.h * (b.w / 4) + 255) / 256;
+            if (bx > 148 * 8) bx = 148 * 8;
+            const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src);
+            uint8_t* d8 = reinterpret_cast<uint8_t*>(oct_ws + b.off);
+            if (k == 1 && fuse_mm)
+                octave_u8_vec_kernel<true><<<dim3(bx, batch), 256, 0, stream>>>(s8, src_stride, a.w, d8, oct_stride, b.h, b.w, mm, n_oct, k);
+            else
+                octave_u8_vec_kernel<false><<<dim3(bx, batch), 256, 0, stream>>>(s8, src_stride, a.w, d8, oct_stride, b.h, b.w, mm, n_oct, k);
+        } else {
+            int bx = (b.h * b.w + 255) / 256;
+            if (bx > 2048) bx = 2048;
+            octave_kernel<T><<<dim3(bx, batch), 256, 0, stream>>>(src, src_stride, a.w, oct_ws + b.off, oct_stride, b.h, b.w, mm, n_oct, k);
+        }
         WBG_CUDA_TRY(cudaGetLastError());
     }
 
