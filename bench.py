@@ -255,14 +255,15 @@ def run_gpu(args):
         model.theta = [-np.inf] * len(model)
     eng = get_engine()
 
-    # ---- synthetic frames, page-locked on the host (frame i of rank r uses seed 1000 + r*B + i)
+    # ---- synthetic frames, page-locked on the host (seeds 1000.., a set of distinct frames cycled to
+    # fill the batch).  Every rank gets the SAME set, rotated by its rank, so the per-GPU work is identical (weak
+    # scaling): the cascade's cost depends on the frame content.
     uniq = min(B, args.unique_frames)
     pinned = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
     frames = pinned.numpy()
-    for i in range(uniq):
-        frames[i] = S.synthetic_frame(1000 + rank * B + i, H, W)
-    for i in range(uniq, B):
-        frames[i] = frames[i % uniq]
+    base = [S.synthetic_frame(1000 + i, H, W) for i in range(uniq)]
+    for i in range(B):
+        frames[i] = base[(i + rank) % uniq]
 
     plan = model._plan(eng, H, W)
     handle = model._device_model()

@@ -36,15 +36,30 @@ template <typename T> __device__ __forceinline__ int mm_encode(T v);
 template <> __device__ __forceinline__ int mm_encode<uint8_t>(uint8_t v) { return (int)v; }
 template <> __device__ __forceinline__ int mm_encode<float>(float v) { return f32_to_ordered(v); }
 
+// block-wide min/max folded into dst with ONE atomic pair per block (every thread of the block must call it)
 __device__ __forceinline__ void block_minmax_commit(int mn, int mx, int2* dst) {
+    __shared__ int s_mn[32], s_mx[32];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&dst->x, mn);
-        atomicMax(&dst->y, mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    __syncthreads();                       // the arrays may still be read by a previous call in the same kernel
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < nwarps ? s_mn[lane] : 0x7fffffff;
+        mx = lane < nwarps ? s_mx[lane] : (int)0x80000000;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        if (lane == 0) {
+            atomicMin(&dst->x, mn);
+            atomicMax(&dst->y, mx);
+        }
     }
 }
 
