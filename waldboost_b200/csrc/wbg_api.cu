@@ -82,15 +82,17 @@ static int env_int(const char* name, int dflt) {
 }
 
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
-    // Tile candidates, largest first.  A big tile keeps the lanes of the sparse late stages fuller (the survivors of
-    // 4096 windows share a CTA) and halves the halo overhead; it must leave room for two CTAs per SM.
+    // Tile candidates in order of preference (measured on B200 with the config B cascade, ms per 64 frames:
+    // 32x64 windows / 512 threads / 3 CTAs per SM 24.9, 32x128 / 512 x 8 slots / 2 CTAs 25.6, 16x64 / 256 / 5 CTAs 29.2).
+    // A larger tile keeps the lanes of the sparse late stages fuller and halves the halo overhead, but fewer
+    // resident CTAs hide less of each tile's barrier and tail latency.
     struct Cand { int TR, TC, threads, wpt, budget; };
-    const Cand cand[] = {{32, 128, 512, 8, 112 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
+    const Cand cand[] = {{32, 64, 512, 4, 74 * 1024}, {32, 128, 512, 8, 112 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
-    int cnum = env_int("WBG_CAS_COMPACT_NUM", 1), cden = env_int("WBG_CAS_COMPACT_DEN", 2);
-    if (cnum < 1 || cden <= cnum) { cnum = 1; cden = 2; }
+    int cnum = env_int("WBG_CAS_COMPACT_NUM", 3), cden = env_int("WBG_CAS_COMPACT_DEN", 4);
+    if (cnum < 1 || cden <= cnum) { cnum = 3; cden = 4; }
     int idx = 0;
     for (auto& c : cand) {
         if (idx++ < skip) continue;
@@ -106,9 +108,9 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
             g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap;
             g->compact_num = cnum;
             g->compact_den = cden;
-            g->round_full = env_int("WBG_CAS_ROUND_FULL", 16);
-            g->round_mid = env_int("WBG_CAS_ROUND_MID", 32);
-            g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 64);
+            g->round_full = env_int("WBG_CAS_ROUND_FULL", 32);
+            g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
+            g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
             return true;
         }
     }

@@ -147,7 +147,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 }
 
 template <bool D2, int THREADS, int WPT>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 2) cascade_kernel(const CascadeParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 3)) cascade_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int ENTRIES = WPT * WARPS;          // (slot, warp) ballot counts, a multiple of 32
     constexpr int EPL = ENTRIES / 32;             // entries scanned per lane of warp 0
@@ -509,6 +509,8 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     } while (0)
     if (g.threads == 512 && g.wpt == 8) {
         if (model->all_d2) WBG_CAS_LAUNCH(true, 512, 8); else WBG_CAS_LAUNCH(false, 512, 8);
+    } else if (g.threads == 512 && g.wpt == 4) {
+        if (model->all_d2) WBG_CAS_LAUNCH(true, 512, 4); else WBG_CAS_LAUNCH(false, 512, 4);
     } else {
         WBG_REQUIRE(g.threads == 256 && g.wpt == 4, "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
         if (model->all_d2) WBG_CAS_LAUNCH(true, 256, 4); else WBG_CAS_LAUNCH(false, 256, 4);
