@@ -813,6 +813,229 @@ static int launch_hist_level(const PyrParams& p, int S, int SM, long long grid, 
     return WBG_EINVAL;
 }
 
+// ------------------------------------------------------------------------------------------------ grad_mag fast kernel
+// level_kernel with every tile dimension a compile-time constant (shrink S, smooth SM, triangle half-width G) and the
+// shortcuts of the grad_hist kernels: uint8 resampling decided in float32 away from integer boundaries, exact
+// float32 gradients for uint8 images, pooled values converted to float64 once for the smoothing sums.
+// Channels: [0] = gradient magnitude normalised by its 2G+1 triangle average (channels.py:30-37), [1..] = grad_hist
+// bins when p.kind == WBG_CH_GRAD_MAG_HIST.
+template <typename T, int S, int SM, int G>
+__global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams p) {
+    constexpr int TU = PYR_TU, TV = PYR_TV;
+    constexpr int PH = TU + 2 * SM, PW = TV + 2 * SM;
+    constexpr int FH = S * PH, FW = S * PW;                 // full-resolution channel pixels
+    constexpr int MH = FH + 2 * G, MW = FW + 2 * G;         // magnitude incl. the triangle halo
+    constexpr int RH = MH + 2, RW = MW + 2;                 // resized pixels incl. the gradient halo
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    int lo = 0, hi = p.n_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.levels[mid].ptile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const LevelDev* __restrict__ L = p.levels + lo;
+    const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
+    const int local = tile_id - L->ptile0;
+    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ou0 = ty * TU, ov0 = tx * TV;
+    const int C = p.C;
+    const bool has_hist = p.kind == WBG_CH_GRAD_MAG_HIST;
+    const int ry0 = S * (ou0 - SM) - G - 1, rx0 = S * (ov0 - SM) - G - 1;
+
+    // shared memory: taps | R | F (normalised magnitude) | union { M + T1 (magnitude, first triangle pass), P (pooled, float64) }
+    TapF* s_tapr = reinterpret_cast<TapF*>(smem_raw);
+    TapF* s_tapc = s_tapr + RH;
+    float* s_R = reinterpret_cast<float*>(s_tapc + RW);        // [RH][RW]
+    float* s_F = s_R + RH * RW;                                // [FH][FW]
+    float* s_M = s_F + FH * FW;                                // [MH][MW]
+    float* s_T1 = s_M + MH * MW;                               // [FH][MW]
+    double* s_P = reinterpret_cast<double*>(s_M);              // [C][PH*PW], written after M / T1 are dead
+
+    const T* __restrict__ src = (L->oct == 0)
+        ? reinterpret_cast<const T*>(p.img) + (long long)frame * p.img_stride
+        : reinterpret_cast<const T*>(p.oct_ws) + (long long)frame * p.oct_stride + L->src_off;
+    const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
+    const bool identity = L->identity != 0;
+
+    for (int i = tid; i < RH + RW; i += PYR_THREADS) {
+        const bool row = i < RH;
+        const Tap t = row ? make_tap(reflect_idx(ry0 + i, nh), L->zoom_r, sh) : make_tap(reflect_idx(rx0 + (i - RH), nw), L->zoom_c, sw);
+        TapF f;
+        f.i0 = t.i0; f.i1 = t.i1; f.w1f = (float)t.w1; f.pad_ = 0.f; f.w0 = t.w0; f.w1 = t.w1;
+        if (row) s_tapr[i] = f; else s_tapc[i - RH] = f;
+    }
+    __syncthreads();
+    // ---- resized tile (channels.py:132)
+    for (int i = tid; i < RH * RW; i += PYR_THREADS) {
+        const int iy = i / RW, ix = i - iy * RW;
+        const TapF* a = s_tapr + iy;
+        const TapF* b = s_tapc + ix;
+        const T* r0p = src + (long long)a->i0 * sw;
+        const T* r1p = src + (long long)a->i1 * sw;
+        const int bi0 = b->i0, bi1 = b->i1;
+        float val;
+        if (identity) {
+            val = (float)__ldg(r0p + bi0);
+        } else {
+            const T q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
+            bool exact = true;
+            val = 0.f;
+            if (sizeof(T) == 1) {
+                const float f00 = (float)q00, f01 = (float)q01, f10 = (float)q10, f11 = (float)q11;
+                const float top = fmaf(b->w1f, f01 - f00, f00), bot = fmaf(b->w1f, f11 - f10, f10);
+                const float r = fmaf(a->w1f, bot - top, top);
+                val = __fadd_rd(r, 12582912.f) - 12582912.f;
+                exact = fabsf((r - val) - 0.5f) > 0.5f - RESAMPLE_DELTA && ((int)q00 | (int)q01 | (int)q10 | (int)q11) != 0;
+            }
+            if (exact) {
+                double t = __dmul_rn(__dmul_rn((double)q00, a->w0), b->w0);
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, a->w0), b->w1));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, a->w1), b->w0));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, a->w1), b->w1));
+                val = finish_resample<T>(t, mm.x, mm.y);
+            }
+        }
+        s_R[i] = val;
+    }
+    __syncthreads();
+
+    // channels.py:16-21; exact in float32 for integer-valued (uint8) images, float64 expression otherwise
+    auto smooth121 = [](float prev, float mid, float next) -> float {
+        if (sizeof(T) == 1) return fmaf(2.f, mid, prev + next);
+        return (float)(2.0 * (double)mid + ((double)prev + (double)next));
+    };
+    auto grad = [&](const float* r, float& gx, float& gy) {       // r = &s_R[iy][ix], 1 <= iy, ix
+        gx = __fsub_rn(smooth121(r[-RW - 1], r[-1], r[RW - 1]), smooth121(r[-RW + 1], r[1], r[RW + 1]));
+        gy = __fsub_rn(smooth121(r[-RW - 1], r[-RW], r[-RW + 1]), smooth121(r[RW - 1], r[RW], r[RW + 1]));
+    };
+    // ---- gradient magnitude on the extended grid (channels.py:31-32), float32 throughout
+    for (int i = tid; i < MH * MW; i += PYR_THREADS) {
+        const int iy = i / MW, ix = i - iy * MW;
+        float gx, gy;
+        grad(s_R + (iy + 1) * RW + ix + 1, gx, gy);
+        s_M[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+    }
+    __syncthreads();
+    if (G > 0) {
+        // ---- triangle normalisation (channels.py:33-36): axis 0 then axis 1, float64 accumulate in scipy's symmetric
+        // order, float32 between the passes
+        double tri[G + 1];
+#pragma unroll
+        for (int k = 0; k <= G; ++k) tri[k] = (double)p.tri[k];
+        for (int i = tid; i < FH * MW; i += PYR_THREADS) {
+            const int iy = i / MW, ix = i - iy * MW;
+            const float* c = s_M + (iy + G) * MW + ix;
+            double acc = (double)c[0] * tri[G];
+#pragma unroll
+            for (int k = -G; k < 0; ++k) acc += ((double)c[k * MW] + (double)c[-k * MW]) * tri[G + k];
+            s_T1[i] = (float)acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < FH * FW; i += PYR_THREADS) {
+            const int iy = i / FW, ix = i - iy * FW;
+            const float* c = s_T1 + iy * MW + ix + G;
+            double acc = (double)c[0] * tri[G];
+#pragma unroll
+            for (int k = -G; k < 0; ++k) acc += ((double)c[k] + (double)c[-k]) * tri[G + k];
+            s_F[i] = __fdiv_rn(s_M[(iy + G) * MW + ix + G], __fadd_rn((float)acc, p.eps));
+        }
+    } else {
+        for (int i = tid; i < FH * FW; i += PYR_THREADS) s_F[i] = s_M[i];
+    }
+    __syncthreads();
+
+    // ---- channels at full resolution + SxS mean (channels.py:136-139); pooled values as float64
+    for (int i = tid; i < PH * PW; i += PYR_THREADS) {
+        const int py = i / PW, px = i - py * PW;
+        const int pu = ou0 - SM + py, pv = ov0 - SM + px;
+        if (pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
+        float gx[S * S], gy[S * S], acc = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < S * S; ++sub) {
+            // order of channels.py:61-64: a00, a10 (next row), a01 (next column), a11
+            const int fy = S * py + (sub & (S - 1)), fx = S * px + (sub >> (S - 1));
+            const float mval = s_F[fy * FW + fx];
+            acc = sub == 0 ? mval : __fadd_rn(acc, mval);
+            if (has_hist) grad(s_R + (fy + G + 1) * RW + fx + G + 1, gx[sub], gy[sub]);
+        }
+        s_P[i] = (double)(S == 2 ? __fmul_rn(acc, 0.25f) : acc);
+        if (has_hist) {
+            for (int bin = 0; bin < p.n_bins; ++bin) {
+                const double cb = p.cs[bin], sb = p.sn[bin];
+                float a2 = 0.f;
+#pragma unroll
+                for (int sub = 0; sub < S * S; ++sub) {
+                    // channels.py:50 under NumPy 2: float64 products and difference, one rounding to float32
+                    const float ch = (float)__dadd_rn(__dmul_rn((double)gx[sub], cb), -__dmul_rn((double)gy[sub], sb));
+                    float val = fmaxf(__fsub_rn(fabsf(ch), p.bias), 0.f);
+                    if (p.full) val = __fmul_rn((float)((ch > 0.f) - (ch < 0.f)), val);
+                    a2 = sub == 0 ? val : __fadd_rn(a2, val);
+                }
+                s_P[(1 + bin) * (PH * PW) + i] = (double)(S == 2 ? __fmul_rn(a2, 0.25f) : a2);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3x3 smoothing with a zero border ring (channels.py:78-90) and the HWC store
+    float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
+    for (int i = tid; i < TU * TV * C; i += PYR_THREADS) {
+        const int c = i % C, pix = i / C;
+        const int oy = pix / TV, ox = pix - oy * TV;
+        const int ou = ou0 + oy, ov = ov0 + ox;
+        if (ou >= u || ov >= v) continue;
+        const double* q = s_P + c * (PH * PW) + (oy + SM) * PW + (ox + SM);
+        float r;
+        if (!SM) {
+            r = (float)q[0];
+        } else if (ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1) {
+            r = 0.f;
+        } else {
+            double a = q[-PW - 1] + 2.0 * q[-PW];
+            a += q[-PW + 1];
+            a += 2.0 * q[-1];
+            a += 4.0 * q[0];
+            a += 2.0 * q[1];
+            a += q[PW - 1];
+            a += 2.0 * q[PW];
+            a += q[PW + 1];
+            r = (float)(a * 0.0625);
+        }
+        out[((long long)ou * v + ov) * C + c] = r;
+    }
+}
+
+template <int S, int SM, int G>
+static constexpr size_t mag_smem_bytes(int C) {
+    constexpr int PH = PYR_TU + 2 * SM, PW = PYR_TV + 2 * SM, FH = S * PH, FW = S * PW, MH = FH + 2 * G, MW = FW + 2 * G;
+    constexpr int RH = MH + 2, RW = MW + 2;
+    const size_t mt = (size_t)(MH * MW + FH * MW) * 4, pp = (size_t)C * PH * PW * 8;
+    return (size_t)(RH + RW) * sizeof(TapF) + (size_t)(RH * RW + FH * FW) * 4 + (mt > pp ? mt : pp) + 32;
+}
+
+template <typename T>
+static int launch_mag_level(const PyrParams& p, int S, int SM, int G, long long grid, cudaStream_t stream, bool* handled) {
+    *handled = true;
+#define WBG_MAG_CASE(SS, MM, GG)                                                                                     \
+    if (S == SS && SM == MM && G == GG) {                                                                            \
+        const size_t smem = mag_smem_bytes<SS, MM, GG>(p.C);                                                         \
+        if (smem > 200 * 1024) { *handled = false; return WBG_OK; }                                                  \
+        WBG_CUDA_TRY(cudaFuncSetAttribute(level_mag_kernel<T, SS, MM, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);                                                               \
+        level_mag_kernel<T, SS, MM, GG><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);                           \
+        wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);                                                                 \
+        WBG_CUDA_TRY(cudaGetLastError());                                                                            \
+        return WBG_OK;                                                                                               \
+    }
+    WBG_MAG_CASE(2, 1, 5) WBG_MAG_CASE(2, 1, 0) WBG_MAG_CASE(2, 0, 5) WBG_MAG_CASE(2, 0, 0)
+    WBG_MAG_CASE(1, 1, 5) WBG_MAG_CASE(1, 1, 0) WBG_MAG_CASE(1, 0, 5) WBG_MAG_CASE(1, 0, 0)
+#undef WBG_MAG_CASE
+    *handled = false;        // other triangle widths: the run-time sized level_kernel
+    return WBG_OK;
+}
+
 static size_t level_smem_bytes(const wbg_channel_opts& o, int C) {
     const int S = o.shrink, hsm = o.smooth == 1 ? 1 : 0;
     const bool has_mag = o.kind != WBG_CH_GRAD_HIST;
@@ -909,6 +1132,11 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
             return WBG_OK;
         }
         return launch_hist_level<T>(p, o.shrink, o.smooth == 1 ? 1 : 0, grid_h, stream);
+    }
+    if (!getenv("WBG_PYR_GENERIC")) {
+        bool handled = false;
+        const int rc = launch_mag_level<T>(p, o.shrink, o.smooth == 1 ? 1 : 0, p.G, grid_h, stream, &handled);
+        if (rc != WBG_OK || handled) return rc;
     }
     const size_t smem = level_smem_bytes(o, plan->C);
     WBG_REQUIRE(smem <= 220 * 1024, "channel pyramid: tile needs %zu bytes of shared memory", smem);
