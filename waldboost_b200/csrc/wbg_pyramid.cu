@@ -668,6 +668,11 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
     __syncthreads();
 
     // ---- P1: resized tile (channels.py:132), one (row, 32-column chunk) per warp iteration
+#ifndef H4_P1_UNROLL
+#define H4_P1_UNROLL 2
+#endif
+    constexpr int kP1Unroll = H4_P1_UNROLL;
+#pragma unroll kP1Unroll
     for (int task = warp; task < 2 * RH; task += H4_WARPS) {
         const int iy = task >> 1, ix = ((task & 1) << 5) + lane;
         const TapF* a = s_tapr + iy;
