@@ -4,13 +4,16 @@
 // (waldboost/training.py:84-96) and Model.get_boxes (waldboost/model.py:136-147) for every level of every frame
 // of a batch in one launch family:
 //
-//   cascade_kernel   one CTA per tile of TR x TC windows.  The (TR+m-1) x (TC+n-1) x C channel patch is staged
-//                    once in shared memory, channel-planar, so that the 32 lanes of a warp (adjacent windows)
-//                    gather adjacent words.  Windows are scored stage by stage in float32 (stage order, like
-//                    `hs += weak.predict_on_image`), rejected with `hs >= theta[t]`, and the surviving windows of
-//                    the CTA are re-packed (ballot + prefix sum, order preserving) after every stage block so
-//                    early exit does not leave idle lanes.  Survivors set a bit in a per-frame window mask and
-//                    store their score in a dense score map.
+//   cascade_kernel   one CTA per tile of TR x TC windows (32 x 64 for the 12x12x4 model).  The (TR+m-1) x (TC+n-1) x C
+//                    channel patch is staged once in shared memory, channel-planar, so that the 32 lanes of a warp
+//                    (adjacent windows) gather adjacent words.  Every thread owns WPT window slots.  The cascade
+//                    runs in rounds of 32..128 stages: within a round each warp scores its slots on its own, stage
+//                    by stage in float32 (stage order, like `hs += weak.predict_on_image`) with the test
+//                    `hs >= theta[t]`; a rejected slot is marked by a NaN score and simply stops mattering.  At the
+//                    end of a round the CTA counts its survivors and, once no more than 3/4 of the slots are live,
+//                    re-packs them (ballot + prefix sum, order preserving) so rejection does not leave idle lanes.
+//                    Survivors of all T stages set a bit in a per-frame window mask and store their score in a
+//                    dense score map.
 //   mask_*/emit_hits popcount prefix sums over the mask give every survivor its rank in the reference's output
 //                    order (frame, level, r, c) -- the stable boolean filtering of model.py:255-258 -- without a
 //                    sort; boxes are produced in the same pass.
@@ -34,7 +37,7 @@ struct CascadeParams {
     int N, T;
     int C, m, n;
     int TR, TC, pitch, plane;
-    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail, flags;
+    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail;
     unsigned* mask;
     long long mask_stride;  // words per frame
     float* score;
@@ -208,9 +211,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         hs[k] = has ? 0.f : CUDART_NAN_F;
     }
 
-    // slot idx = tid + k*stride; after a re-pack the survivors are spread over as few warps as possible (4 slots per
-    // thread) so the per-stage overhead is shared by 4 windows, and the warps left without slots retire
-    int n_slots = nwin, n_alive = nwin, t = 0, round = 0, stride = THREADS;
+    int n_slots = nwin, n_alive = nwin, t = 0, round = 0;
     unsigned my_weak = 0;
     while (t < p.T && n_alive > 0) {
         // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
@@ -221,9 +222,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         if (__any_sync(0xffffffffu, mine)) {
             // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            if (WPT >= 8 && first + 4 * THREADS < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + 2 * THREADS < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + THREADS < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
             else run_round<D2, 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
         }
         // ---- how many windows of the tile are still alive
@@ -275,11 +276,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         }
         __syncthreads();
         n_slots = n_alive;
-        stride = (p.flags & 2) ? min(THREADS, (((n_slots + 3) >> 2) + 31) & ~31) : THREADS;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            const int idx = tid + k * stride;
-            const bool has = (k < 4 || stride == THREADS) && tid < stride && idx < n_slots;
+            const int idx = tid + k * THREADS;
+            const bool has = idx < n_slots;
             wa[k] = tile_base + 4u * (has ? (unsigned)s_woff[idx] : 0u);
             hs[k] = has ? s_score[idx] : CUDART_NAN_F;
         }
@@ -497,7 +497,6 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const CascadeGeom& g = model->geom;
     p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
-    { const char* f = getenv("WBG_CAS_FLAGS"); p.flags = f ? atoi(f) : 0; }
     const int smem = g.smem_bytes;
     if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));

@@ -5,12 +5,19 @@
 // uint8 truncation of channels.py:132 changes a pixel by 1).
 //
 // Launch family per batch:
-//   minmax_kernel     per-frame min/max of the input (skimage.resize clips to the input range)
-//   octave_kernel     octave chain, 2x2 average of the *image* (channels.py:93-101, :55-64) + its min/max
-//   level_kernel      ONE launch for all levels of all frames; each CTA produces a 16x32 tile of final channel
-//                     pixels and fuses resize -> gradients -> grad_hist / grad_mag -> 2x2 shrink -> 3x3 smooth
-//                     (channels.py:132-142) through shared memory, reading the octave image and writing the
-//                     channel map exactly once.
+//   minmax / octave kernels   per-frame min/max of the input (skimage.resize clips to the input range) and the octave
+//                             chain, 2x2 truncating means of the *image* (channels.py:93-101, :55-64); uint8 frames
+//                             with 8-byte aligned rows use octave_u8_vec_kernel (8-byte loads, frame min/max fused)
+//   level kernels             ONE launch for all levels of all frames; each CTA produces a tile of final channel
+//                             pixels and fuses resize -> gradients -> grad_hist / grad_mag -> 2x2 shrink -> 3x3 smooth
+//                             (channels.py:132-142) through shared memory, reading the octave image and writing the
+//                             channel map exactly once:
+//       level_hist4_u8_kernel     uint8 frames, default 4-bin grad_hist, shrink 2, smooth 1 (BASELINE configs A/B/D/E)
+//       level_hist_kernel<T,S,SM> every other grad_hist setting and float32 frames
+//       level_mag_kernel<T,S,SM,G> grad_mag and grad_mag + grad_hist (config C) for norm = 5 or no normalisation
+//       level_kernel<T>           run-time sized fallback (other triangle widths)
+//   All of them produce the reference's values bit for bit on the test inputs; the faster ones only skip float64
+//   work where the float32 result is provably the same.
 #include <math_constants.h>
 #include <stdlib.h>
 
