@@ -37,7 +37,10 @@ enum { WBG_U8 = 0, WBG_F32 = 1 };
 enum {
     WBG_CH_GRAD_HIST = 0,     /* waldboost.channels.grad_hist  (channels.py:40-52)  C = n_bins      */
     WBG_CH_GRAD_MAG = 1,      /* waldboost.channels.grad_mag   (channels.py:30-37)  C = 1           */
-    WBG_CH_GRAD_MAG_HIST = 2  /* concat(grad_mag, grad_hist)     C = 1+n_bins */
+    WBG_CH_GRAD_MAG_HIST = 2, /* concat(grad_mag, grad_hist)     C = 1+n_bins */
+    /* integer channels of the reference's FPGA variant (uint8 frames only; values 0..255 delivered as float32) */
+    WBG_CH_FPGA_HIST4_U1 = 3, /* waldboost.fpga.channels.grad_hist_4_u1 (fpga/channels.py:29-52)   C = 4  */
+    WBG_CH_FPGA_MAG_U1 = 4    /* waldboost.fpga.channels.grad_mag_u1    (fpga/channels.py:55-66)   C = 1  */
 };
 
 #define WBG_MAX_BINS 16

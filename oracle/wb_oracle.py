@@ -108,6 +108,38 @@ def grad_hist(image, n_bins=4, full=False, bias=0):
     return (np.sign(chns) * val) if full else val
 
 
+def _fpga_grad(arr):
+    """fpga/channels.py:5-27 -- integer Sobel stencils; Numba's stencil leaves the 1-pixel border at cval = 0 and
+    widens uint8 operands to int64; the results are stored as int32 (fpga/channels.py:40-43)."""
+    a = np.asarray(arr).astype(np.int64)
+    dx = np.zeros(a.shape, np.int64)
+    dy = np.zeros(a.shape, np.int64)
+    if a.shape[0] >= 3 and a.shape[1] >= 3:
+        c = lambda dr, dc: a[1 + dr:a.shape[0] - 1 + dr, 1 + dc:a.shape[1] - 1 + dc]
+        dx[1:-1, 1:-1] = -(c(-1, -1) + 2 * c(0, -1) + c(1, -1)) + c(-1, 1) + 2 * c(0, 1) + c(1, 1)
+        dy[1:-1, 1:-1] = -(c(-1, -1) + 2 * c(-1, 0) + c(-1, 1)) + c(1, -1) + 2 * c(1, 0) + c(1, 1)
+    return dx.astype(np.int32), dy.astype(np.int32)
+
+
+def grad_hist_4_u1(image):
+    """fpga/channels.py:29-52 -- dx, 0.5dx-0.5dy, dy, 0.5dx+0.5dy (float64, truncated toward zero on the int32 store),
+    then min(|y| // 4, 255) as uint8."""
+    dx, dy = _fpga_grad(image)
+    y = np.empty(dx.shape + (4,), np.int32)
+    y[..., 0] = dx
+    y[..., 1] = np.trunc(0.5 * dx - 0.5 * dy)
+    y[..., 2] = dy
+    y[..., 3] = np.trunc(0.5 * dx + 0.5 * dy)
+    return np.fmin(np.abs(y) // 4, 255).astype(np.uint8)
+
+
+def grad_mag_u1(image):
+    """fpga/channels.py:55-66 -- max(|dx|, |dy|) // 4 clamped to 255, uint8."""
+    dx, dy = _fpga_grad(image)
+    y = np.maximum(np.abs(dx), np.abs(dy))[..., None]
+    return np.fmin(y // 4, 255).astype(np.uint8)
+
+
 def grad_mag_hist(image, n_bins=9, norm=5, eps=1e-3):
     """Composite 1+n_bins channel function used by BASELINE config C: the reference has no
     such function; it is defined as the concatenation of the two reference functions on the same image."""
@@ -141,6 +173,15 @@ def smooth_image_3d(arr):
     """channels.py:78-90.  3x3 [1 2 1]x[1 2 1]: Numba types int*float32 as float64, so the nine terms are
     accumulated in float64 in source order, divided by 16 and rounded to float32; the stencil leaves the
     1-pixel border at cval=0."""
+    if np.asarray(arr).dtype.kind in "ui":
+        # integer channel maps (fpga channels): int64 sums, true division, truncating store into the input dtype
+        a = np.asarray(arr).astype(np.int64)
+        out = np.zeros(a.shape, np.int64)
+        if a.shape[0] >= 3 and a.shape[1] >= 3:
+            c = lambda dr, dc: a[1 + dr:a.shape[0] - 1 + dr, 1 + dc:a.shape[1] - 1 + dc]
+            out[1:-1, 1:-1] = (c(-1, -1) + 2 * c(-1, 0) + c(-1, 1) + 2 * c(0, -1) + 4 * c(0, 0) + 2 * c(0, 1)
+                               + c(1, -1) + 2 * c(1, 0) + c(1, 1))
+        return (out / 16).astype(np.asarray(arr).dtype)
     a = np.asarray(arr, F32).astype(F64)
     out = np.zeros(a.shape, F64)
     if a.shape[0] >= 3 and a.shape[1] >= 3:

@@ -112,7 +112,28 @@ def config_B_detect():
     print("config B (540x960 crop): hits", scores.size, "n_loc", n_loc, "n_weak", n_weak, "eval_cost", n_weak / n_loc)
 
 
+def fpga_pyramid():
+    """integer channels of the reference's FPGA variant (waldboost/fpga/channels.py) through channel_pyramid."""
+    from waldboost.fpga import channels as fch
+    frame = S.synthetic_frame(1000, 96, 128)
+    noise = S.noise_frame(3, 70, 90)
+    cfgs = {"hist4u1_s2_sm1": dict(shrink=2, n_per_oct=4, smooth=1, channels=fch.grad_hist_4_u1),
+            "hist4u1_s1_sm0": dict(shrink=1, n_per_oct=2, smooth=0, channels=fch.grad_hist_4_u1),
+            "magu1_s2_sm1": dict(shrink=2, n_per_oct=3, smooth=1, channels=fch.grad_mag_u1),
+            "magu1_s1_sm1": dict(shrink=1, n_per_oct=2, smooth=1, channels=fch.grad_mag_u1)}
+    out = {"frame": frame, "noise": noise}
+    for name, opts in cfgs.items():
+        for tag, img in (("frame", frame), ("noise", noise)):
+            for k, (chns, scale) in enumerate(rch.channel_pyramid(img, opts)):
+                out[f"{name}/{tag}/{k}"] = chns
+                out[f"{name}/{tag}/{k}/scale"] = np.float64(scale)
+    np.savez_compressed(os.path.join(HERE, "fpga_pyramid.npz"), **out)
+    print("fpga fixtures:", len(out))
+
+
 def main():
+    if "--fpga" in sys.argv:
+        return fpga_pyramid()
     if "--config-b" in sys.argv:
         return config_B()
     if "--config-b-detect" in sys.argv:

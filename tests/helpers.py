@@ -9,7 +9,8 @@ from waldboost_b200 import synthetic as S
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-ORACLE_FN = {"grad_hist": O.grad_hist, "grad_mag": O.grad_mag, "grad_mag_hist": O.grad_mag_hist}
+ORACLE_FN = {"grad_hist": O.grad_hist, "grad_mag": O.grad_mag, "grad_mag_hist": O.grad_mag_hist,
+             "grad_hist_4_u1": O.grad_hist_4_u1, "grad_mag_u1": O.grad_mag_u1}
 
 
 def oracle_opts(channel_opts):
@@ -18,6 +19,8 @@ def oracle_opts(channel_opts):
     from waldboost_b200.channels import resolve_channels
     spec = resolve_channels(channel_opts["channels"])
     kind = spec["name"]
+    if kind in ("grad_hist_4_u1", "grad_mag_u1"):
+        return dict(channel_opts, channels=ORACLE_FN[kind])
     if kind == "grad_hist":
         fn = functools.partial(O.grad_hist, n_bins=spec["n_bins"], full=spec["full"], bias=spec["bias"])
     elif kind == "grad_mag":

@@ -462,3 +462,47 @@ def test_pipelined_batch_matches_frame_by_frame():
     M.theta = [-np.inf] * len(M)                      # dense profile: every window is a hit (> 4096 per chunk)
     out2, hits2 = M.detect_batch(frames[:20], return_hits=True)
     assert hits2.size == 20 * sum(int(c) for c in [len(M.detect(frames[0]))]) and np.all(np.diff(hits2["frame"]) >= 0)
+
+
+# ------------------------------------------------------------------------------------------- FPGA integer channels
+FPGA_CFG = {
+    "hist4u1_s2_sm1": dict(shrink=2, n_per_oct=4, smooth=1, channels=wb.fpga.grad_hist_4_u1),
+    "hist4u1_s1_sm0": dict(shrink=1, n_per_oct=2, smooth=0, channels=wb.fpga.grad_hist_4_u1),
+    "magu1_s2_sm1": dict(shrink=2, n_per_oct=3, smooth=1, channels=wb.fpga.grad_mag_u1),
+    "magu1_s1_sm1": dict(shrink=1, n_per_oct=2, smooth=1, channels=wb.fpga.grad_mag_u1),
+}
+
+
+@pytest.mark.parametrize("name", list(FPGA_CFG))
+@pytest.mark.parametrize("tag", ["frame", "noise"])
+def test_fpga_channels_vs_reference_golden(name, tag):
+    """waldboost.fpga.channels.grad_hist_4_u1 / grad_mag_u1 through channel_pyramid: uint8 maps, bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "fpga_pyramid.npz"))
+    got = list(CH.channel_pyramid(g[tag], FPGA_CFG[name]))
+    n_ref = len([k for k in g.files if k.startswith(f"{name}/{tag}/") and k.endswith("/scale")])
+    assert len(got) == n_ref > 0
+    for k, (chns, scale) in enumerate(got):
+        ref = g[f"{name}/{tag}/{k}"]
+        assert chns.dtype == np.uint8 and np.array_equal(chns, ref), f"level {k}"
+        assert scale == float(g[f"{name}/{tag}/{k}/scale"])
+
+
+def test_fpga_channels_direct_detect_and_errors(tmp_path):
+    img = S.synthetic_frame(1004, 200, 260)
+    assert np.array_equal(wb.fpga.grad_hist_4_u1(img), O.grad_hist_4_u1(img))
+    assert np.array_equal(wb.fpga.grad_mag_u1(img), O.grad_mag_u1(img))
+    with pytest.raises(TypeError):
+        wb.fpga.grad_hist_4_u1(img.astype(np.float32))
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=wb.fpga.grad_hist_4_u1)
+    M = make_model((12, 12, 4), opts, 32, 2, img, keep_total=2e-2)
+    Cs = oracle_cascade(M)
+    dt = M.detect(img)
+    boxes, scores, _ = Cs.detect(img)
+    assert scores.size > 0 and np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
+    assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak)
+    path = str(tmp_path / "fpga.pb")                      # the .pb names the reference's function
+    M.save(path)
+    M2 = wb.load(path)
+    assert M2.channel_opts["channels"] is wb.fpga.grad_hist_4_u1
+    with pytest.raises(Exception):                         # float32 frames are rejected for the integer channels
+        M.detect(img.astype(np.float32))

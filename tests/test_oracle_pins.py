@@ -218,3 +218,25 @@ def test_oracle_config_B_model_equals_reference_golden():
     boxes, scores, _ = Cs.detect(crop)
     assert np.array_equal(boxes, g["boxes"]) and np.array_equal(scores, g["scores"])
     assert (Cs.n_loc, Cs.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
+
+
+FPGA_CFG = {
+    "hist4u1_s2_sm1": dict(shrink=2, n_per_oct=4, smooth=1, channels=O.grad_hist_4_u1),
+    "hist4u1_s1_sm0": dict(shrink=1, n_per_oct=2, smooth=0, channels=O.grad_hist_4_u1),
+    "magu1_s2_sm1": dict(shrink=2, n_per_oct=3, smooth=1, channels=O.grad_mag_u1),
+    "magu1_s1_sm1": dict(shrink=1, n_per_oct=2, smooth=1, channels=O.grad_mag_u1),
+}
+
+
+@pytest.mark.parametrize("name", list(FPGA_CFG))
+@pytest.mark.parametrize("tag", ["frame", "noise"])
+def test_oracle_fpga_channels_equal_reference_golden(name, tag):
+    """integer channels of the reference's FPGA variant (waldboost/fpga/channels.py) through channel_pyramid."""
+    g = np.load(os.path.join(GOLDEN, "fpga_pyramid.npz"))
+    levels = list(O.channel_pyramid(g[tag], FPGA_CFG[name]))
+    n_ref = len([k for k in g.files if k.startswith(f"{name}/{tag}/") and k.endswith("/scale")])
+    assert len(levels) == n_ref > 0
+    for k, (chns, scale) in enumerate(levels):
+        ref = g[f"{name}/{tag}/{k}"]
+        assert chns.dtype == np.uint8 == ref.dtype and np.array_equal(chns, ref), f"level {k}"
+        assert scale == float(g[f"{name}/{tag}/{k}/scale"])

@@ -11,6 +11,7 @@ The CUDA library (libwbg.so, include/wbg.h) is required: there is no CPU fallbac
 import numpy as np
 
 from . import channels
+from . import fpga
 from .boxes import Boxes, concatenate
 from .model import Model
 from .training import DTree

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libwbg.so")
 
 WBG_OK, WBG_EINVAL, WBG_ECAP, WBG_ECUDA, WBG_ENOMEM = 0, -1, -2, -3, -4
 WBG_U8, WBG_F32 = 0, 1
-WBG_CH_GRAD_HIST, WBG_CH_GRAD_MAG, WBG_CH_GRAD_MAG_HIST = 0, 1, 2
+WBG_CH_GRAD_HIST, WBG_CH_GRAD_MAG, WBG_CH_GRAD_MAG_HIST, WBG_CH_FPGA_HIST4_U1, WBG_CH_FPGA_MAG_U1 = 0, 1, 2, 3, 4
 WBG_MAX_BINS, WBG_MAX_NORM, WBG_MAX_CHANNELS = 16, 8, 17
 ABI_VERSION = 2
 

@@ -26,8 +26,11 @@ def _direct(kind_fn, image, **kw):
     from .engine import get_engine
     if not isinstance(image, np.ndarray) or image.ndim != 2:
         raise ValueError("channel functions take a 2-D numpy image")
-    img = np.ascontiguousarray(image).astype(np.float32)   # reference: image.astype("f") (channels.py:31,41)
     spec = resolve_channels(functools.partial(kind_fn, **kw) if kw else kind_fn)
+    if spec.get("integer"):
+        img = np.ascontiguousarray(image)                      # integer channels work on the uint8 image itself
+    else:
+        img = np.ascontiguousarray(image).astype(np.float32)   # reference: image.astype("f") (channels.py:31,41)
     opts = dict(shrink=1, n_per_oct=1, smooth=0, channels=None)
     levels = get_engine().channel_levels(img, opts, spec, max_levels=1)
     return levels[0][0]
@@ -56,6 +59,14 @@ _DEFAULTS = {
 }
 
 
+_EXTRA = {}          # functions registered by sub-packages (waldboost_b200.fpga): fn -> (spec defaults, channel count)
+
+
+def register_channel_function(fn, defaults, channels, integer=False):
+    _DEFAULTS[fn] = dict(defaults)
+    _EXTRA[fn] = dict(channels=channels, integer=integer)
+
+
 def resolve_channels(fn):
     """Map `channel_opts["channels"]` to the kernel variant: one of the functions above, optionally wrapped in
     functools.partial with keyword arguments.  Anything else raises -- no CPU fallback."""
@@ -68,8 +79,10 @@ def resolve_channels(fn):
         base = base.func
     if base not in _DEFAULTS:
         raise TypeError(f"channel function {fn!r} has no CUDA implementation; supported: "
-                        "waldboost_b200.channels.grad_hist, grad_mag, grad_mag_hist "
-                        "(optionally functools.partial with keyword arguments)")
+                        "waldboost_b200.channels.grad_hist, grad_mag, grad_mag_hist, waldboost_b200.fpga.grad_hist_4_u1, "
+                        "grad_mag_u1 (optionally functools.partial with keyword arguments)")
+    if base in _EXTRA and kw:
+        raise TypeError(f"{base.__name__}() takes no keyword arguments")
     spec = dict(_DEFAULTS[base])
     for k, v in kw.items():
         if k not in spec or (base is grad_hist and k in ("norm", "eps")) or (base is grad_mag and k in ("n_bins", "full", "bias")):
@@ -78,10 +91,15 @@ def resolve_channels(fn):
     if spec["norm"] is None:
         spec["norm"] = 0
     spec["name"] = base.__name__
+    spec["integer"] = bool(_EXTRA.get(base, {}).get("integer"))
+    if base in _EXTRA:
+        spec["channels"] = _EXTRA[base]["channels"]
     return spec
 
 
 def channel_count(spec):
+    if "channels" in spec:
+        return spec["channels"]
     return {N.WBG_CH_GRAD_HIST: spec["n_bins"], N.WBG_CH_GRAD_MAG: 1, N.WBG_CH_GRAD_MAG_HIST: 1 + spec["n_bins"]}[spec["kind"]]
 
 

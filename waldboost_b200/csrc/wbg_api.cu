@@ -122,6 +122,8 @@ static int channels_of(const wbg_channel_opts* o) {
         case WBG_CH_GRAD_HIST: return o->n_bins;
         case WBG_CH_GRAD_MAG: return 1;
         case WBG_CH_GRAD_MAG_HIST: return 1 + o->n_bins;
+        case WBG_CH_FPGA_HIST4_U1: return 4;
+        case WBG_CH_FPGA_MAG_U1: return 1;
         default: return -1;
     }
 }
@@ -141,10 +143,10 @@ extern "C" int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_op
     WBG_REQUIRE(H >= 1 && W >= 1, "wbg_plan_create: bad image size %dx%d", H, W);
     WBG_REQUIRE(opts->shrink == 1 || opts->shrink == 2, "Shrink factor must be integer 1 <= shrink <= 2");
     WBG_REQUIRE(opts->n_per_oct >= 1 && opts->n_per_oct <= 64, "wbg_plan_create: bad n_per_oct %d", opts->n_per_oct);
-    WBG_REQUIRE(opts->kind >= WBG_CH_GRAD_HIST && opts->kind <= WBG_CH_GRAD_MAG_HIST, "wbg_plan_create: unknown channel kind %d", opts->kind);
-    if (opts->kind != WBG_CH_GRAD_MAG)
+    WBG_REQUIRE(opts->kind >= WBG_CH_GRAD_HIST && opts->kind <= WBG_CH_FPGA_MAG_U1, "wbg_plan_create: unknown channel kind %d", opts->kind);
+    if (opts->kind == WBG_CH_GRAD_HIST || opts->kind == WBG_CH_GRAD_MAG_HIST)
         WBG_REQUIRE(opts->n_bins >= 1 && opts->n_bins <= WBG_MAX_BINS, "wbg_plan_create: n_bins must be in 1..%d", WBG_MAX_BINS);
-    if (opts->kind != WBG_CH_GRAD_HIST)
+    if (opts->kind == WBG_CH_GRAD_MAG || opts->kind == WBG_CH_GRAD_MAG_HIST)
         WBG_REQUIRE(opts->norm <= WBG_MAX_NORM, "wbg_plan_create: grad_mag norm must be <= %d", WBG_MAX_NORM);
     WBG_REQUIRE(win_m >= 0 && win_n >= 0 && win_m <= 256 && win_n <= 256, "wbg_plan_create: bad window %dx%d", win_m, win_n);
 

@@ -1048,6 +1048,141 @@ static int launch_mag_level(const PyrParams& p, int S, int SM, int G, long long 
     return WBG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ FPGA integer channels
+// waldboost/fpga/channels.py through channel_pyramid: everything after the resampling is integer arithmetic --
+// 3x3 Sobel stencils whose 1-pixel border is 0 (Numba stencil), |y| // 4 clamped to 255 as uint8, 2x2 mean and 3x3
+// smoothing with truncating stores (channels.py:55-64, :78-90 on a uint8 array).  Values are delivered as float32.
+template <int S, int SM>
+__global__ void __launch_bounds__(PYR_THREADS) level_fpga_kernel(const PyrParams p) {
+    constexpr int TU = PYR_TU, TV = PYR_TV;
+    constexpr int PH = TU + 2 * SM, PW = TV + 2 * SM, FH = S * PH, FW = S * PW, RH = FH + 2, RW = FW + 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.x / p.tiles_per_frame;
+    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
+    int lo = 0, hi = p.n_levels - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (p.levels[mid].ptile0 <= tile_id) lo = mid; else hi = mid - 1;
+    }
+    const LevelDev* __restrict__ L = p.levels + lo;
+    const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
+    const int local = tile_id - L->ptile0;
+    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ou0 = ty * TU, ov0 = tx * TV;
+    const int C = p.C;
+    const bool hist = p.kind == WBG_CH_FPGA_HIST4_U1;
+    const int ry0 = S * (ou0 - SM) - 1, rx0 = S * (ov0 - SM) - 1;
+
+    TapF* s_tapr = reinterpret_cast<TapF*>(smem_raw);
+    TapF* s_tapc = s_tapr + RH;
+    int* s_R = reinterpret_cast<int*>(s_tapc + RW);           // [RH][RW] resized pixels
+    int* s_P = s_R + RH * RW;                                 // [C][PH*PW] pooled uint8 channel values
+    const uint8_t* __restrict__ src = (L->oct == 0)
+        ? reinterpret_cast<const uint8_t*>(p.img) + (long long)frame * p.img_stride
+        : reinterpret_cast<const uint8_t*>(p.oct_ws) + (long long)frame * p.oct_stride + L->src_off;
+    const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
+    const bool identity = L->identity != 0;
+
+    for (int i = tid; i < RH + RW; i += PYR_THREADS) {
+        const bool row = i < RH;
+        // positions outside the resized image are never used (the stencil border is 0): clamp them to a valid tap
+        const Tap t = row ? make_tap(min(max(ry0 + i, 0), nh - 1), L->zoom_r, sh) : make_tap(min(max(rx0 + (i - RH), 0), nw - 1), L->zoom_c, sw);
+        TapF f;
+        f.i0 = t.i0; f.i1 = t.i1; f.w1f = (float)t.w1; f.pad_ = 0.f; f.w0 = t.w0; f.w1 = t.w1;
+        if (row) s_tapr[i] = f; else s_tapc[i - RH] = f;
+    }
+    __syncthreads();
+    for (int i = tid; i < RH * RW; i += PYR_THREADS) {
+        const int iy = i / RW, ix = i - iy * RW;
+        const TapF* a = s_tapr + iy;
+        const TapF* b = s_tapc + ix;
+        const uint8_t* r0p = src + (long long)a->i0 * sw;
+        const uint8_t* r1p = src + (long long)a->i1 * sw;
+        const unsigned q00 = __ldg(r0p + b->i0), q01 = __ldg(r0p + b->i1), q10 = __ldg(r1p + b->i0), q11 = __ldg(r1p + b->i1);
+        int val;
+        if (identity) {
+            val = (int)q00;
+        } else {
+            const float f00 = (float)q00, f01 = (float)q01, f10 = (float)q10, f11 = (float)q11;
+            const float top = fmaf(b->w1f, f01 - f00, f00), bot = fmaf(b->w1f, f11 - f10, f10);
+            const float r = fmaf(a->w1f, bot - top, top);
+            const float fl = __fadd_rd(r, 12582912.f) - 12582912.f;
+            val = (int)fl;
+            if (fabsf((r - fl) - 0.5f) > 0.5f - RESAMPLE_DELTA && (q00 | q01 | q10 | q11) != 0u) {
+                double t = __dmul_rn(__dmul_rn((double)q00, a->w0), b->w0);
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, a->w0), b->w1));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, a->w1), b->w0));
+                t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, a->w1), b->w1));
+                val = (int)finish_resample<uint8_t>(t, mm.x, mm.y);
+            }
+        }
+        s_R[i] = val;
+    }
+    __syncthreads();
+
+    for (int i = tid; i < PH * PW; i += PYR_THREADS) {
+        const int py = i / PW, px = i - py * PW;
+        const int pu = ou0 - SM + py, pv = ov0 - SM + px;
+        if (pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
+        int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int sub = 0; sub < S * S; ++sub) {
+            const int fy = S * py + (sub & (S - 1)), fx = S * px + (sub >> (S - 1));     // tile-relative full-res pixel
+            const int gy_ = S * pu + (sub & (S - 1)), gx_ = S * pv + (sub >> (S - 1));   // position in the resized image
+            int dx = 0, dy = 0;
+            if (gy_ > 0 && gy_ < nh - 1 && gx_ > 0 && gx_ < nw - 1) {                    // fpga/channels.py:5-27, border = 0
+                const int* r = s_R + (fy + 1) * RW + fx + 1;
+                dx = -(r[-RW - 1] + 2 * r[-1] + r[RW - 1]) + r[-RW + 1] + 2 * r[1] + r[RW + 1];
+                dy = -(r[-RW - 1] + 2 * r[-RW] + r[-RW + 1]) + r[RW - 1] + 2 * r[RW] + r[RW + 1];
+            }
+            if (hist) {
+                // fpga/channels.py:44-48: 0.5*dx -+ 0.5*dy is exact in float64; the int32 store truncates toward zero
+                acc[0] += min(abs(dx) >> 2, 255);
+                acc[1] += min(abs((dx - dy) / 2) >> 2, 255);
+                acc[2] += min(abs(dy) >> 2, 255);
+                acc[3] += min(abs((dx + dy) / 2) >> 2, 255);
+            } else {
+                acc[0] += min(max(abs(dx), abs(dy)) >> 2, 255);                           // fpga/channels.py:56-63
+            }
+        }
+        for (int c = 0; c < C; ++c) s_P[c * (PH * PW) + i] = S == 2 ? acc[c] >> 2 : acc[c];   // channels.py:61-64, truncating
+    }
+    __syncthreads();
+
+    float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
+    for (int i = tid; i < TU * TV * C; i += PYR_THREADS) {
+        const int c = i % C, pix = i / C;
+        const int oy = pix / TV, ox = pix - oy * TV;
+        const int ou = ou0 + oy, ov = ov0 + ox;
+        if (ou >= u || ov >= v) continue;
+        const int* q = s_P + c * (PH * PW) + (oy + SM) * PW + (ox + SM);
+        int r;
+        if (!SM) r = q[0];
+        else if (ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1) r = 0;
+        else r = (q[-PW - 1] + 2 * q[-PW] + q[-PW + 1] + 2 * q[-1] + 4 * q[0] + 2 * q[1] + q[PW - 1] + 2 * q[PW] + q[PW + 1]) >> 4;
+        out[((long long)ou * v + ov) * C + c] = (float)r;
+    }
+}
+
+static int launch_fpga_level(const PyrParams& p, int S, int SM, long long grid, cudaStream_t stream) {
+#define WBG_FPGA_CASE(SS, MM)                                                                                          \
+    if (S == SS && SM == MM) {                                                                                         \
+        constexpr int PH = PYR_TU + 2 * MM, PW = PYR_TV + 2 * MM, RH = SS * PH + 2, RW = SS * PW + 2;                  \
+        const size_t smem = (size_t)(RH + RW) * sizeof(TapF) + (size_t)(RH * RW + p.C * PH * PW) * 4 + 16;            \
+        WBG_CUDA_TRY(cudaFuncSetAttribute(level_fpga_kernel<SS, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);                                                                 \
+        level_fpga_kernel<SS, MM><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);                                   \
+        wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);                                                                   \
+        WBG_CUDA_TRY(cudaGetLastError());                                                                              \
+        return WBG_OK;                                                                                                 \
+    }
+    WBG_FPGA_CASE(2, 1) WBG_FPGA_CASE(2, 0) WBG_FPGA_CASE(1, 1) WBG_FPGA_CASE(1, 0)
+#undef WBG_FPGA_CASE
+    wbg_set_error("channel pyramid: unsupported shrink %d", S);
+    return WBG_EINVAL;
+}
+
 static size_t level_smem_bytes(const wbg_channel_opts& o, int C) {
     const int S = o.shrink, hsm = o.smooth == 1 ? 1 : 0;
     const bool has_mag = o.kind != WBG_CH_GRAD_HIST;
@@ -1115,9 +1250,9 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
     p.img = img; p.img_stride = img_stride; p.oct_ws = oct_ws; p.oct_stride = oct_stride; p.minmax = mm; p.n_oct = n_oct;
     p.levels = plan->d_levels; p.n_levels = (int)plan->levels.size(); p.tiles_per_frame = plan->ptiles;
     p.chns = chns; p.chn_stride = plan->chn_floats;
-    p.C = plan->C; p.S = o.shrink; p.smooth = o.smooth; p.kind = o.kind; p.n_bins = o.kind == WBG_CH_GRAD_MAG ? 0 : o.n_bins;
+    p.C = plan->C; p.S = o.shrink; p.smooth = o.smooth; p.kind = o.kind; p.n_bins = (o.kind == WBG_CH_GRAD_HIST || o.kind == WBG_CH_GRAD_MAG_HIST) ? o.n_bins : 0;
     p.full = o.full; p.bias = o.bias; p.eps = o.eps;
-    p.G = (o.kind != WBG_CH_GRAD_HIST && o.norm > 1) ? o.norm : 0;
+    p.G = ((o.kind == WBG_CH_GRAD_MAG || o.kind == WBG_CH_GRAD_MAG_HIST) && o.norm > 1) ? o.norm : 0;
     if (p.G > 0) {
         // channels.py:11-13 -- ([1..n+1..1]).astype(f) / sum, float32 division
         const int n = p.G;
@@ -1128,6 +1263,10 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
 
     const long long grid_h = (long long)plan->ptiles * batch;
     WBG_REQUIRE(grid_h <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid_h);
+    if (o.kind == WBG_CH_FPGA_HIST4_U1 || o.kind == WBG_CH_FPGA_MAG_U1) {
+        WBG_REQUIRE(sizeof(T) == 1, "the FPGA integer channels (grad_hist_4_u1, grad_mag_u1) take uint8 frames");
+        return launch_fpga_level(p, o.shrink, o.smooth == 1 ? 1 : 0, grid_h, stream);
+    }
     if (o.kind == WBG_CH_GRAD_HIST) {
         // the orientation table of the default 4-bin histogram: cos/sin = (1,0), (c,s), (6.1e-17,1), (-s,c)
         p.fast4 = (o.n_bins == 4 && !o.full && o.cos_t[0] == 1.0 && o.sin_t[0] == 0.0 && o.sin_t[2] == 1.0 &&

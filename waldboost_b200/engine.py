@@ -46,7 +46,7 @@ def make_channel_opts(channel_opts, spec, max_levels=0):
     o.max_levels = int(max_levels)
     if o.n_bins > N.WBG_MAX_BINS:
         raise ValueError(f"n_bins must be <= {N.WBG_MAX_BINS}")
-    if o.n_bins > 0:
+    if o.n_bins > 0 and spec["kind"] in (N.WBG_CH_GRAD_HIST, N.WBG_CH_GRAD_MAG_HIST):
         max_theta = 2 * np.pi if spec["full"] else np.pi
         theta = np.linspace(0, max_theta, o.n_bins + 1)
         cs, sn = np.cos(theta[:-1]), np.sin(theta[:-1])
@@ -254,7 +254,9 @@ class Engine:
         dev = self.upload_images(image[None])
         chns = self.pyramid(dev, plan)
         host = chns[0].cpu().numpy()
-        return [(lv.copy(), s) for lv, s in zip(self.split_levels(host, plan), plan.scales)]
+        # the reference's integer channel functions yield uint8 maps (fpga/channels.py:52,63)
+        cast = (lambda a: a.astype(np.uint8)) if spec.get("integer") else (lambda a: a.copy())
+        return [(cast(lv), s) for lv, s in zip(self.split_levels(host, plan), plan.scales)]
 
     # ------------------------------------------------------------------------------------------- cascade
     def _meta(self, B, n_levels, slot=""):

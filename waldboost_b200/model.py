@@ -20,13 +20,15 @@ from .training import DTree
 
 # names under which channel functions are stored in .pb files (model.py:302).  Functions that exist in the
 # reference are written with the reference's module path so either implementation can load the file.
-_REFERENCE_NAMES = {"grad_hist": "waldboost.channels.grad_hist", "grad_mag": "waldboost.channels.grad_mag"}
+_REFERENCE_NAMES = {("channels", "grad_hist"), ("channels", "grad_mag"),
+                    ("fpga.channels", "grad_hist_4_u1"), ("fpga.channels", "grad_mag_u1")}
 
 
 def symbol_name(s):
     """reference model.py:23-24, with reference-compatible names for the functions both packages have."""
-    if getattr(s, "__module__", None) == _channels.__name__ and s.__name__ in _REFERENCE_NAMES:
-        return _REFERENCE_NAMES[s.__name__]
+    mod = getattr(s, "__module__", "") or ""
+    if mod.startswith(__package__ + ".") and (mod[len(__package__) + 1:], s.__name__) in _REFERENCE_NAMES:
+        return "waldboost." + mod[len(__package__) + 1:] + "." + s.__name__
     return s.__module__ + "." + s.__qualname__
 
 
@@ -181,7 +183,8 @@ class Model:
             k = int(counts[0, lvl])
             h = hits[pos:pos + k]
             pos += k
-            yield maps[lvl].copy(), plan.scales[lvl], (h["r"].astype(np.int64), h["c"].astype(np.int64), h["score"].copy())
+            chn = maps[lvl].astype(np.uint8) if self._spec().get("integer") else maps[lvl].copy()
+            yield chn, plan.scales[lvl], (h["r"].astype(np.int64), h["c"].astype(np.int64), h["score"].copy())
 
     @staticmethod
     def _boxes_from_hits(h):
