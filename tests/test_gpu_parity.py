@@ -445,20 +445,20 @@ def test_sample_mode_predict():
 def test_pipelined_batch_matches_frame_by_frame():
     """batches larger than one pipeline chunk (16 frames) go through the two-stream H2D/compute pipeline: same hits,
     same order, same counters as frame-by-frame detect(); also exercises the hit-buffer overflow path of a chunk."""
-    frames = S.synthetic_frames(37, 96, 128)
+    frames = S.synthetic_frames(21, 96, 128)
     M = make_model((12, 12, 4), OPTS_A, 24, 2, frames[0], keep_total=5e-2, calib_levels=2)
     M.reset()
     out, hits = M.detect_batch(frames, return_hits=True)
     batch_stats = (M.n_loc, M.n_weak)
     M.reset()
     pos = 0
-    for b in range(37):
+    for b in range(21):
         one = M.detect(frames[b])
         k = len(one)
         assert np.array_equal(hits["frame"][pos:pos + k], np.full(k, b))
         assert np.array_equal(hits["score"][pos:pos + k], one.get_field("scores")) and np.array_equal(out[b].get(), one.get())
         pos += k
-    assert pos == hits.size > 37 and (M.n_loc, M.n_weak) == batch_stats
+    assert pos == hits.size > 21 and (M.n_loc, M.n_weak) == batch_stats
     M.theta = [-np.inf] * len(M)                      # dense profile: every window is a hit (> 4096 per chunk)
     out2, hits2 = M.detect_batch(frames[:20], return_hits=True)
     assert hits2.size == 20 * sum(int(c) for c in [len(M.detect(frames[0]))]) and np.all(np.diff(hits2["frame"]) >= 0)

@@ -1,6 +1,7 @@
 """Host-side driver of libwbg: plans, device buffers and launches.  PyTorch is used only as the device-memory and
 stream carrier; every computation is a C-ABI call into the CUDA library (include/wbg.h).  No CPU fallback."""
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -316,12 +317,14 @@ class Engine:
                 return self._read_hits(hits_t, n_hits), counts, stats
             hit_cap = n_hits  # WBG_ECAP semantics: only the first hit_cap were stored -> re-run with room for all
 
-    def run_frames(self, model_handle, plan, images, chunk=16):
+    def run_frames(self, model_handle, plan, images, chunk=None):
         """detect() over host frames [B,H,W] as a two-slot pipeline: the frames go to the device in chunks, and the
         host->device copy of chunk k+1 (copy engine) overlaps the pyramid + cascade kernels of chunk k (two streams,
         one buffer set each).  Returns (hits with batch-global frame indices, level_counts [B,L], stats [B,2])."""
         torch = self.torch
         B = int(images.shape[0])
+        if chunk is None:
+            chunk = int(os.environ.get("WBG_PIPE_CHUNK", "8"))
         if B <= chunk:
             dev = self.upload_images(images)
             chns = self.pyramid(dev, plan)
