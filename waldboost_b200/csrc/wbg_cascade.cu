@@ -9,7 +9,7 @@
 //                    (adjacent windows) gather adjacent words.  Every thread owns WPT window slots.  The cascade
 //                    runs in rounds of 32..128 stages: within a round each warp scores its slots on its own, stage
 //                    by stage in float32 (stage order, like `hs += weak.predict_on_image`) with the test
-//                    `hs >= theta[t]`; a rejected slot is marked by a NaN score and simply stops mattering.  At the
+//                    `hs >= theta[t]`; a rejected slot just carries alive = 0 and stops mattering.  At the
 //                    end of a round the CTA counts its survivors and, once no more than 3/4 of the slots are live,
 //                    re-packs them (ballot + prefix sum, order preserving) so rejection does not leave idle lanes.
 //                    Survivors of all T stages set a bit in a per-frame window mask and store their score in a
@@ -37,7 +37,7 @@ struct CascadeParams {
     int N, T;
     int C, m, n;
     int TR, TC, pitch, plane;
-    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail;
+    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail, pack;
     unsigned* mask;
     long long mask_stride;  // words per frame
     float* score;
@@ -82,18 +82,22 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
 // form a dependency chain.  Dead slots keep executing with their results ignored (their lanes are idle anyway while
 // the warp is live).  `last[k]` is the index after the last stage the slot entered alive (n_weak, model.py:252).
 // Generic topology: follow the left/right links of the node records (training.py:88-95).
+// 1.0f / 0.0f compare results (SASS FSET.BF): they keep the leaf selection and the liveness bookkeeping on the FMA
+// pipe.  On sm_100 FSETP / FSEL / SEL all issue to the ALU pipe (one warp instruction per 2 cycles per scheduler); a
+// loop body made only of them is bound by that pipe while the FMA pipe idles.
+__device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.le.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+
 template <bool D2, int NK, int WPT>
-__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], int t, int t_end,
-                                          unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
+__device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], float (&alive)[WPT],
+                                          int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
                                           const float* __restrict__ thetas) {
-    // A rejected window is marked by hs = NaN: NaN + p stays NaN and NaN >= theta is false for every theta
-    // (including -inf = "no test", model.py:253), so dead slots need no flag.  Live scores are never NaN because
-    // the depth-2 fast path is only taken for models whose predictions are all finite (wbg_model_create).
+    // alive[k] is 1.0f while the slot's window is live and 0.0f afterwards (or when the slot is empty); a dead slot
+    // keeps executing with its results ignored (its lane is idle anyway while the warp is live).
     if (D2) {
-        int passed[NK];                 // index after the last stage whose test the slot passed
-        bool live0[NK];
+        float entered[NK];              // stages the slot entered alive in this round (model.py:252)
 #pragma unroll
-        for (int k = 0; k < NK; ++k) { passed[k] = t; live0[k] = hs[k] == hs[k]; }
+        for (int k = 0; k < NK; ++k) entered[k] = 0.f;
 #pragma unroll 4
         for (int s = t; s < t_end; ++s) {
             const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
@@ -101,7 +105,6 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             const float thr0 = __int_as_float(A.y), thr1 = __int_as_float(A.w), thr4 = __int_as_float(B.y);
             const float p2 = __int_as_float(B.z), p3 = __int_as_float(B.w);
             const float p5 = __int_as_float(Cc.x), p6 = __int_as_float(Cc.y), theta = __int_as_float(Cc.z);
-            const int s1 = s + 1;
             float x0[NK], xa[NK], xb[NK];
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
@@ -113,17 +116,16 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             for (int k = 0; k < NK; ++k) {
                 const float pa = (xa[k] <= thr1) ? p2 : p3;        // training.py:92 -- left iff X <= threshold
                 const float pb = (xb[k] <= thr4) ? p5 : p6;
-                const float h = hs[k] + ((x0[k] <= thr0) ? pa : pb);   // float32 accumulation in stage order (model.py:251)
-                const bool ok = h >= theta;                        // model.py:255; true for every live score when theta = -inf
-                hs[k] = ok ? h : CUDART_NAN_F;
-                passed[k] = ok ? s1 : passed[k];
+                const float m0 = fset_le(x0[k], thr0);
+                // m0 ? pa : pb on the FMA pipe, exact for finite leaves: (-m0*pb + pb) is pb or +0, then + m0*pa
+                const float pr = __fmaf_rn(m0, pa, __fmaf_rn(-m0, pb, pb));
+                entered[k] += alive[k];
+                hs[k] += pr;                                       // float32 accumulation in stage order (model.py:251)
+                alive[k] *= fset_ge(hs[k], theta);                 // model.py:255; theta = -inf passes every finite score
             }
         }
-        // model.py:252 -- n_weak += windows entering each stage: a slot that entered the round alive ran the stages it
-        // passed plus the one that rejected it
 #pragma unroll
-        for (int k = 0; k < NK; ++k)
-            my_weak += live0[k] ? (unsigned)(passed[k] - t + ((hs[k] == hs[k]) ? 0 : 1)) : 0u;
+        for (int k = 0; k < NK; ++k) my_weak += (unsigned)entered[k];
     } else {
         const float* tile = nullptr;
         asm("cvta.shared.u64 %0, %1;" : "=l"(tile) : "l"((unsigned long long)tile_base));
@@ -133,16 +135,16 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             const bool test = theta != -CUDART_INF_F;
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
-                if (hs[k] == hs[k]) {
+                if (alive[k] != 0.f) {
                     const float* w = tile + ((wa[k] - tile_base) >> 2);
                     NodeDev nd = load_node(nb);
                     while (nd.left >= 0) {
                         const float x = w[nd.off];
                         nd = load_node(nb + ((x <= nd.thr) ? nd.left : nd.right));
                     }
-                    const float h = hs[k] + nd.pred;
+                    hs[k] += nd.pred;
                     ++my_weak;
-                    hs[k] = (!test || h >= theta) ? h : CUDART_NAN_F;
+                    alive[k] = (!test || hs[k] >= theta) ? 1.f : 0.f;
                 }
             }
         }
@@ -201,38 +203,41 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
     unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
     asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
     unsigned wa[WPT];
-    float hs[WPT];                     // running score of the slot's window; NaN = no window / rejected
+    float hs[WPT], alive[WPT];         // running score of the slot's window; alive = 1.0f / 0.0f (empty or rejected)
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
         const int idx = tid + k * THREADS;
         const bool has = idx < nwin;
         const int lr = has ? idx / cols_valid : 0, lc = has ? idx - lr * cols_valid : 0;
         wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
-        hs[k] = has ? 0.f : CUDART_NAN_F;
+        hs[k] = 0.f;
+        alive[k] = has ? 1.f : 0.f;
     }
 
-    int n_slots = nwin, n_alive = nwin, t = 0, round = 0;
+    // slot idx = tid + k*stride.  After a re-pack the survivors are laid out `p.pack` slots per thread over as few
+    // warps as needed, so the per-stage record loads keep being shared by several windows of a thread.
+    int n_slots = nwin, n_alive = nwin, t = 0, round = 0, stride = THREADS;
     unsigned my_weak = 0;
     while (t < p.T && n_alive > 0) {
         // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
         const int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
         bool mine = false;
 #pragma unroll
-        for (int k = 0; k < WPT; ++k) mine |= hs[k] == hs[k];
+        for (int k = 0; k < WPT; ++k) mine |= alive[k] != 0.f;
         if (__any_sync(0xffffffffu, mine)) {
             // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (WPT >= 8 && first + 4 * THREADS < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + 2 * THREADS < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + THREADS < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else run_round<D2, 1, WPT>(tile_base, wa, hs, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            else run_round<D2, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
         }
         // ---- how many windows of the tile are still alive
         unsigned bal[WPT];
         int wcnt = 0;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            bal[k] = __ballot_sync(0xffffffffu, hs[k] == hs[k]);
+            bal[k] = __ballot_sync(0xffffffffu, alive[k] != 0.f);
             wcnt += __popc(bal[k]);
         }
         const int par = round % 3;
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            if (hs[k] == hs[k]) {
+            if (alive[k] != 0.f) {
                 const int pos = s_pre[k * WARPS + warp] + __popc(bal[k] & ((1u << lane) - 1u));
                 s_woff[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
                 s_score[pos] = hs[k];
@@ -276,19 +281,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         }
         __syncthreads();
         n_slots = n_alive;
+        if (p.pack > 0) stride = min(THREADS, ((n_slots + p.pack - 1) / p.pack + 31) & ~31);
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
-            const int idx = tid + k * THREADS;
-            const bool has = idx < n_slots;
+            const int idx = tid + k * stride;
+            const bool has = tid < stride && idx < n_slots;
             wa[k] = tile_base + 4u * (has ? (unsigned)s_woff[idx] : 0u);
-            hs[k] = has ? s_score[idx] : CUDART_NAN_F;
+            hs[k] = has ? s_score[idx] : 0.f;
+            alive[k] = has ? 1.f : 0.f;
         }
     }
 
     // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
-        if (hs[k] == hs[k]) {
+        if (alive[k] != 0.f) {
             const int wo = (int)((wa[k] - tile_base) >> 2);
             const int lr = wo / pitch, lc = wo - lr * pitch;
             const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
@@ -497,6 +504,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const CascadeGeom& g = model->geom;
     p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
+    p.pack = g.pack > g.wpt ? g.wpt : g.pack;
     const int smem = g.smem_bytes;
     if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));

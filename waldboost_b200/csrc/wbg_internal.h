@@ -45,6 +45,7 @@ struct CascadeGeom {
     int list_cap;      // capacity of the re-pack lists (windows): threads * wpt / 2
     int compact_num, compact_den;   // re-pack when alive * den <= slots * num   (num/den <= 1/2)
     int round_full, round_mid, round_tail;   // stages per round while slots > threads / > 64 / else
+    int pack;                                // slots per thread after a re-pack (0 = keep one slot column per thread)
 };
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g);
 
