@@ -643,7 +643,8 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
     __shared__ __align__(16) TapF s_tapc[RW];
     __shared__ __align__(16) float s_R[RH * RW];
     __shared__ __align__(16) float2 s_P02[PH * PW];     // pooled bins 0 and 2 (exact in float32)
-    __shared__ __align__(16) double2 s_P13[PH * PW];    // pooled bins 1 and 3 as float64 for the smoothing sums
+    __shared__ __align__(16) double s_P1[PH * PW];      // pooled bin 1 as float64 for the smoothing sums
+    __shared__ __align__(16) double s_P3[PH * PW];      // pooled bin 3
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x / p.tiles_per_frame;
     const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
@@ -679,6 +680,9 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
 #define H4_P1_UNROLL 2
 #endif
     constexpr int kP1Unroll = H4_P1_UNROLL;
+    // the column taps of a lane's two columns stay in registers for the whole phase
+    const int c0i0 = s_tapc[lane].i0, c0i1 = s_tapc[lane].i1, c1i0 = s_tapc[32 + lane].i0, c1i1 = s_tapc[32 + lane].i1;
+    const float c0w = s_tapc[lane].w1f, c1w = s_tapc[32 + lane].w1f;
 #pragma unroll kP1Unroll
     for (int task = warp; task < 2 * RH; task += H4_WARPS) {
         const int iy = task >> 1, ix = ((task & 1) << 5) + lane;
@@ -686,14 +690,14 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
         const TapF* b = s_tapc + ix;
         const uint8_t* __restrict__ r0p = src + (long long)a->i0 * sw;
         const uint8_t* __restrict__ r1p = src + (long long)a->i1 * sw;
-        const int bi0 = b->i0, bi1 = b->i1;
+        const int bi0 = (task & 1) ? c1i0 : c0i0, bi1 = (task & 1) ? c1i1 : c0i1;
         float val;
         if (identity) {
             val = u8_to_f32(__ldg(r0p + bi0));
         } else {
             const unsigned q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
             const float f00 = u8_to_f32(q00), f01 = u8_to_f32(q01), f10 = u8_to_f32(q10), f11 = u8_to_f32(q11);
-            const float wx = b->w1f, wy = a->w1f;
+            const float wx = (task & 1) ? c1w : c0w, wy = a->w1f;
             const float top = fmaf(wx, f01 - f00, f00), bot = fmaf(wx, f11 - f10, f10);
             const float r = fmaf(wy, bot - top, top);
             val = __fadd_rd(r, 12582912.f) - 12582912.f;            // floor(r) for |r| < 2^22
@@ -764,40 +768,74 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
         const float a1 = __fadd_rn(__fadd_rn(__fadd_rn(ch1[0][0], ch1[1][0]), ch1[0][1]), ch1[1][1]);
         const float a3 = __fadd_rn(__fadd_rn(__fadd_rn(ch3[0][0], ch3[1][0]), ch3[0][1]), ch3[1][1]);
         s_P02[py * PW + px] = make_float2(a0 * 0.25f, a2 * 0.25f);
-        s_P13[py * PW + px] = make_double2((double)__fmul_rn(a1, 0.25f), (double)__fmul_rn(a3, 0.25f));
+        s_P1[py * PW + px] = (double)__fmul_rn(a1, 0.25f);
+        s_P3[py * PW + px] = (double)__fmul_rn(a3, 0.25f);
     }
     __syncthreads();
 
-    // ---- P3: 3x3 smoothing (channels.py:78-90), zero border ring, float4 HWC store
+    // ---- P3: 3x3 smoothing (channels.py:78-90), zero border ring, float4 HWC store.  One lane per column and TWO
+    // vertically adjacent outputs per lane: the pair shares 2 of its 3 pooled rows, so 12 instead of 18 values are
+    // read from shared memory per plane.
     float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
-    for (int oy = warp; oy < H4_TU; oy += H4_WARPS) {
-        const int ox = lane;
-        const int ou = ou0 + oy, ov = ov0 + ox;
-        if (ox >= H4_TV || ou >= u || ov >= v) continue;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!(ou == 0 || ov == 0 || ou == u - 1 || ov == v - 1)) {
-            const float2* q = s_P02 + (oy + 1) * PW + (ox + 1);
-            const float2 m00 = q[-PW - 1], m01 = q[-PW], m02 = q[-PW + 1], m10 = q[-1], m11 = q[0], m12 = q[1];
-            const float2 m20 = q[PW - 1], m21 = q[PW], m22 = q[PW + 1];
-            // multiples of 1/4 below 2^16: every partial sum is exact, so the order is free
-            r.x = (fmaf(4.f, m11.x, fmaf(2.f, (m01.x + m10.x) + (m12.x + m21.x), (m00.x + m02.x) + (m20.x + m22.x)))) * 0.0625f;
-            r.z = (fmaf(4.f, m11.y, fmaf(2.f, (m01.y + m10.y) + (m12.y + m21.y), (m00.y + m02.y) + (m20.y + m22.y)))) * 0.0625f;
-            if (r.z == 0.f && r.x != 0.f) r.z = hist4_exact_bin2(s_R, oy, ox, p.cs[2], p.sn[2]);
-            const double2* d = s_P13 + (oy + 1) * PW + (ox + 1);
-            const double2 d00 = d[-PW - 1], d01 = d[-PW], d02 = d[-PW + 1], d10 = d[-1], d11 = d[0], d12 = d[1];
-            const double2 d20 = d[PW - 1], d21 = d[PW], d22 = d[PW + 1];
-            double a = d00.x + 2.0 * d01.x, b = d00.y + 2.0 * d01.y;       // source order of channels.py:80-82, float64
-            a += d02.x;        b += d02.y;
-            a += 2.0 * d10.x;  b += 2.0 * d10.y;
-            a += 4.0 * d11.x;  b += 4.0 * d11.y;
-            a += 2.0 * d12.x;  b += 2.0 * d12.y;
-            a += d20.x;        b += d20.y;
-            a += 2.0 * d21.x;  b += 2.0 * d21.y;
-            a += d22.x;        b += d22.y;
-            r.y = (float)(a * 0.0625);
-            r.w = (float)(b * 0.0625);
+    for (int j = warp; j < H4_TU / 2; j += H4_WARPS) {
+        const int ox = lane, ov = ov0 + ox;
+        const int oyA = 2 * j, ouA = ou0 + oyA;
+        if (ox >= H4_TV || ov >= v || ouA >= u) continue;
+        const bool hasB = ouA + 1 < u;
+        const bool colring = ov == 0 || ov == v - 1;
+        const bool ringA = colring || ouA == 0 || ouA == u - 1;
+        const bool ringB = colring || ouA + 1 == u - 1;          // ouA + 1 >= 1, so only the last row can be ring
+        float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = rA;
+        if (!(ringA && (ringB || !hasB))) {
+            const int base = oyA * PW + ox;                      // halo coordinates: row oyA + 1 - 1, column ox + 1 - 1
+            {
+                const float2* q = s_P02 + base;
+                float2 m[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) m[a][b] = q[a * PW + b];
+                // multiples of 1/4 below 2^16: every partial sum is exact, so the order is free
+                auto smooth2 = [&](float4& r) {
+                    r.x = fmaf(4.f, m[1][1].x, fmaf(2.f, (m[0][1].x + m[1][0].x) + (m[1][2].x + m[2][1].x), (m[0][0].x + m[0][2].x) + (m[2][0].x + m[2][2].x))) * 0.0625f;
+                    r.z = fmaf(4.f, m[1][1].y, fmaf(2.f, (m[0][1].y + m[1][0].y) + (m[1][2].y + m[2][1].y), (m[0][0].y + m[0][2].y) + (m[2][0].y + m[2][2].y))) * 0.0625f;
+                };
+                smooth2(rA);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) { m[0][b] = m[1][b]; m[1][b] = m[2][b]; m[2][b] = q[3 * PW + b]; }
+                smooth2(rB);
+            }
+            auto smooth_f64 = [&](const double* d, float& outA, float& outB) {
+                double x[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) x[a][b] = d[a * PW + b];
+                auto sum9 = [&]() -> float {                      // source order of channels.py:80-82, float64
+                    double acc = x[0][0] + 2.0 * x[0][1];
+                    acc += x[0][2];
+                    acc += 2.0 * x[1][0];
+                    acc += 4.0 * x[1][1];
+                    acc += 2.0 * x[1][2];
+                    acc += x[2][0];
+                    acc += 2.0 * x[2][1];
+                    acc += x[2][2];
+                    return (float)(acc * 0.0625);
+                };
+                outA = sum9();
+#pragma unroll
+                for (int b = 0; b < 3; ++b) { x[0][b] = x[1][b]; x[1][b] = x[2][b]; x[2][b] = d[3 * PW + b]; }
+                outB = sum9();
+            };
+            smooth_f64(s_P1 + base, rA.y, rB.y);
+            smooth_f64(s_P3 + base, rA.w, rB.w);
+            if (ringA) rA = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ringB) rB = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!ringA && rA.z == 0.f && rA.x != 0.f) rA.z = hist4_exact_bin2(s_R, oyA, ox, p.cs[2], p.sn[2]);
+            if (!ringB && hasB && rB.z == 0.f && rB.x != 0.f) rB.z = hist4_exact_bin2(s_R, oyA + 1, ox, p.cs[2], p.sn[2]);
         }
-        *reinterpret_cast<float4*>(out + ((long long)ou * v + ov) * 4) = r;
+        *reinterpret_cast<float4*>(out + ((long long)ouA * v + ov) * 4) = rA;
+        if (hasB) *reinterpret_cast<float4*>(out + ((long long)(ouA + 1) * v + ov) * 4) = rB;
     }
 }
 
