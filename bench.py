@@ -345,7 +345,10 @@ def run_gpu(args):
     r_cas = roof("cascade_kernel", cas_b, "cascade_kernel")
     dominant = r_cas if (r_cas and r_pyr and r_cas["ms_per_launch"] > r_pyr["ms_per_launch"]) else (r_pyr or r_cas)
 
-    launches_per_step = 2 + (plan.info.n_octaves - 1) + 1 + 4   # minmax_init, minmax, octaves, level | cascade, 2 scans, emit
+    # kernels of libwbg per step: minmax_init, [minmax unless fused into the first octave step: uint8 frames with even
+    # height and a width that is a multiple of 8], octave steps, level kernel | cascade kernel, 2 mask scans, emit_hits
+    fused_minmax = W % 8 == 0 and H % 2 == 0 and plan.info.n_octaves > 1
+    launches_per_step = 1 + (0 if fused_minmax else 1) + (plan.info.n_octaves - 1) + 1 + 4
     n_weak_all = sum_over_ranks(float(n_weak))
     if rank == 0:
         line = {
