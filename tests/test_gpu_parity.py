@@ -126,7 +126,7 @@ def _oracle_levels(frame, opts):
     return list(O.channel_pyramid(frame, oracle_opts(opts)))
 
 
-@pytest.mark.parametrize("depth,stages", [(2, 64), (1, 16), (3, 24), (4, 40)])
+@pytest.mark.parametrize("depth,stages", [(2, 64), (1, 16), (3, 24), (4, 40), (5, 12)])   # canonical depth-2 records, complete depth-4 records (depth 1, 3, 4), generic node records (depth 5)
 @pytest.mark.parametrize("profile", ["dense", "wald"])
 def test_cascade_on_oracle_channels(depth, stages, profile):
     """given identical channels: survivor sets, float32 scores, n_loc, n_weak bit-exact (facts 1, 7, 8)."""

@@ -317,7 +317,7 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 extern "C" void wbg_model_destroy(wbg_model* m) {
     if (!m) return;
     cudaFree(m->d_feature); cudaFree(m->d_threshold); cudaFree(m->d_left); cudaFree(m->d_right);
-    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2);
+    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_dk4);
     delete m;
 }
 
@@ -339,6 +339,8 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
     std::vector<NodeDev> nodes((size_t)T * N);
     std::vector<StageD2> d2((size_t)T);
     bool all_d2 = T > 0 && T <= D2_MAX_STAGES;
+    std::vector<StageDK4> dk4((size_t)T);
+    bool all_dk4 = T > 0;
     for (int t = 0; t < T; ++t) {
         const int nn = d->n_nodes[t];
         WBG_REQUIRE(nn >= 1 && nn <= N, "wbg_model_create: stage %d has %d nodes (max_nodes %d)", t, nn, N);
@@ -388,11 +390,42 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
             }
         }
         all_d2 = all_d2 && is_d2;
+        // complete depth-4 embedding (heap order); needs depth <= 4 and finite leaf values
+        if (all_dk4) {
+            StageDK4& s = dk4[t];
+            const NodeDev* nd = &nodes[(size_t)t * N];
+            bool ok = true;
+            // iterative expansion: heap position -> original node (or -1-leaf marker)
+            int at[31];
+            at[0] = 0;
+            for (int i = 0; i < 15 && ok; ++i) {
+                const int k = at[i];
+                if (Lf[k] >= 0) {                         // internal node of the original tree
+                    s.node[i] = make_int2(4 * nd[k].off, __builtin_bit_cast(int, nd[k].thr));
+                    at[2 * i + 1] = Lf[k];
+                    at[2 * i + 2] = Rt[k];
+                } else {                                  // a leaf above the last level: always go left, same value below
+                    const float inf = INFINITY;
+                    s.node[i] = make_int2(0, __builtin_bit_cast(int, inf));
+                    at[2 * i + 1] = k;
+                    at[2 * i + 2] = k;
+                }
+            }
+            for (int i = 15; i < 31 && ok; ++i) {
+                const int k = at[i];
+                if (Lf[k] >= 0 || !isfinite(P[k])) ok = false;      // deeper than 4 levels, or a non-finite leaf
+                else s.leaf[i - 15] = P[k];
+            }
+            s.theta = d->theta[t];
+            s.pad_ = 0;
+            all_dk4 = all_dk4 && ok;
+        }
     }
+    if (all_d2) all_dk4 = false;
 
     wbg_model* m = new (std::nothrow) wbg_model();
     if (!m) { wbg_set_error("out of host memory"); return WBG_ENOMEM; }
-    m->m = d->win_m; m->n = d->win_n; m->C = d->channels; m->T = T; m->N = N; m->geom = g; m->all_d2 = all_d2;
+    m->m = d->win_m; m->n = d->win_n; m->C = d->channels; m->T = T; m->N = N; m->geom = g; m->all_d2 = all_d2; m->all_dk4 = all_dk4;
     cudaError_t e = cudaGetDevice(&m->device);
     if (e == cudaSuccess && T > 0) {
         const size_t TN = (size_t)T * N;
@@ -404,6 +437,7 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
         if (e == cudaSuccess) e = upload(&m->d_theta, d->theta, (size_t)T);
         if (e == cudaSuccess) e = upload(&m->d_nodes, nodes.data(), TN);
         if (e == cudaSuccess && all_d2) e = upload(&m->d_d2, d2.data(), (size_t)T);
+        if (e == cudaSuccess && all_dk4) e = upload(&m->d_dk4, dk4.data(), (size_t)T);
     }
     if (e != cudaSuccess) {
         wbg_set_error("wbg_model_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));

@@ -33,6 +33,7 @@ struct CascadeParams {
     const LevelDev* levels;
     int n_levels, tiles_per_frame;
     const NodeDev* nodes;
+    const StageDK4* dk4;
     const float* theta;
     int N, T;
     int C, m, n;
@@ -88,10 +89,47 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
 __device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.le.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 __device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
-template <bool D2, int NK, int WPT>
+enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2 };
+
+template <int MODE, int NK, int WPT>
 __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], float (&alive)[WPT],
                                           int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
-                                          const float* __restrict__ thetas) {
+                                          const float* __restrict__ thetas, const StageDK4* __restrict__ dk4) {
+    constexpr bool D2 = MODE == MODE_D2;
+    if (MODE == MODE_DK4) {
+        // complete depth-4 stages in heap order: the root comes through the uniform path, levels 1..3 and the leaf are
+        // lane-dependent 8- / 4-byte reads of the 192-byte stage record (a handful of distinct addresses per warp,
+        // served by L1); every load is unconditional, so there is no divergence and the slots of a thread overlap.
+        float entered[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) entered[k] = 0.f;
+#pragma unroll 2
+        for (int s = t; s < t_end; ++s) {
+            const StageDK4* __restrict__ rec = dk4 + s;
+            const int2 root = __ldg(&rec->node[0]);
+            const float theta = __ldg(&rec->theta);
+            int idx[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) idx[k] = (lds_f32(wa[k] + (unsigned)root.x) <= __int_as_float(root.y)) ? 1 : 2;
+#pragma unroll
+            for (int lvl = 1; lvl < 4; ++lvl) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const int2 nd = __ldg(&rec->node[idx[k]]);
+                    idx[k] = 2 * idx[k] + ((lds_f32(wa[k] + (unsigned)nd.x) <= __int_as_float(nd.y)) ? 1 : 2);   // training.py:92
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                entered[k] += alive[k];
+                hs[k] += __ldg(&rec->leaf[idx[k] - 15]);           // float32 accumulation in stage order (model.py:251)
+                alive[k] *= fset_ge(hs[k], theta);                 // model.py:255
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) my_weak += (unsigned)entered[k];
+        return;
+    }
     // alive[k] is 1.0f while the slot's window is live and 0.0f afterwards (or when the slot is empty); a dead slot
     // keeps executing with its results ignored (its lane is idle anyway while the warp is live).
     if (D2) {
@@ -151,7 +189,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
     }
 }
 
-template <bool D2, int THREADS, int WPT>
+template <int MODE, int THREADS, int WPT>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 3)) cascade_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int ENTRIES = WPT * WARPS;          // (slot, warp) ballot counts, a multiple of 32
@@ -227,10 +265,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         if (__any_sync(0xffffffffu, mine)) {
             // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<D2, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + 2 * stride < n_slots) run_round<D2, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else if (first + stride < n_slots) run_round<D2, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
-            else run_round<D2, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta);
+            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (first + 2 * stride < n_slots) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (first + stride < n_slots) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
         }
         // ---- how many windows of the tile are still alive
         unsigned bal[WPT];
@@ -494,7 +532,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
 
     CascadeParams p;
     p.chns = chns; p.chn_stride = chn_stride; p.levels = d_levels; p.n_levels = n_levels; p.tiles_per_frame = tiles_per_frame;
-    p.nodes = model->d_nodes; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
+    p.nodes = model->d_nodes; p.dk4 = model->d_dk4; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
     p.C = model->C; p.m = model->m; p.n = model->n;
     p.TR = model->geom.TR; p.TC = model->geom.TC; p.pitch = model->geom.pitch; p.plane = model->geom.plane;
     p.mask = w.mask; p.mask_stride = windows / 32; p.score = w.score; p.score_stride = windows; p.stats = stats;
@@ -508,20 +546,27 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const int smem = g.smem_bytes;
     if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
-#define WBG_CAS_LAUNCH(D2V, TH, WP)                                                                                          \
+#define WBG_CAS_LAUNCH(MODEV, TH, WP)                                                                                        \
     do {                                                                                                                     \
-        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<D2V, TH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+        WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<MODEV, TH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
         wbg_prof_begin(WBG_PROF_CASCADE_KERNEL, stream);                                                                     \
-        cascade_kernel<D2V, TH, WP><<<(unsigned)grid, TH, smem, stream>>>(p);                                                \
+        cascade_kernel<MODEV, TH, WP><<<(unsigned)grid, TH, smem, stream>>>(p);                                              \
+    } while (0)
+#define WBG_CAS_LAUNCH_MODE(TH, WP)                                                       \
+    do {                                                                                  \
+        if (model->all_d2) WBG_CAS_LAUNCH(MODE_D2, TH, WP);                               \
+        else if (model->all_dk4 && !getenv("WBG_CAS_GENERIC")) WBG_CAS_LAUNCH(MODE_DK4, TH, WP); \
+        else WBG_CAS_LAUNCH(MODE_GENERIC, TH, WP);                                        \
     } while (0)
     if (g.threads == 512 && g.wpt == 8) {
-        if (model->all_d2) WBG_CAS_LAUNCH(true, 512, 8); else WBG_CAS_LAUNCH(false, 512, 8);
+        WBG_CAS_LAUNCH_MODE(512, 8);
     } else if (g.threads == 512 && g.wpt == 4) {
-        if (model->all_d2) WBG_CAS_LAUNCH(true, 512, 4); else WBG_CAS_LAUNCH(false, 512, 4);
+        WBG_CAS_LAUNCH_MODE(512, 4);
     } else {
         WBG_REQUIRE(g.threads == 256 && g.wpt == 4, "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
-        if (model->all_d2) WBG_CAS_LAUNCH(true, 256, 4); else WBG_CAS_LAUNCH(false, 256, 4);
+        WBG_CAS_LAUNCH_MODE(256, 4);
     }
+#undef WBG_CAS_LAUNCH_MODE
 #undef WBG_CAS_LAUNCH
     wbg_prof_end(WBG_PROF_CASCADE_KERNEL, stream);
     WBG_CUDA_TRY(cudaGetLastError());

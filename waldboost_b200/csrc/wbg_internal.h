@@ -101,6 +101,17 @@ struct __align__(16) StageD2 {
 };
 constexpr int D2_MAX_STAGES = 1280;  // 61,440 bytes of __constant__
 
+// One stage as a COMPLETE depth-4 tree in heap order (node i -> children 2i+1, 2i+2) for trees of depth <= 4 that are
+// not canonical depth-2 stages: 15 internal nodes, 16 leaves.  A leaf of the original tree that sits higher up is
+// expanded into a subtree whose internal nodes always go left (threshold +inf) and whose leaves all carry its value.
+struct __align__(16) StageDK4 {
+    int2 node[15];        // {byte offset inside the planar patch, threshold bits}
+    float theta;
+    int pad_;
+    float leaf[16];
+};
+static_assert(sizeof(StageDK4) == 192, "StageDK4 layout");
+
 struct wbg_model {
     int m = 0, n = 0, C = 0, T = 0, N = 0;
     CascadeGeom geom{};
@@ -115,6 +126,8 @@ struct wbg_model {
     float* d_theta = nullptr;
     NodeDev* d_nodes = nullptr;   // [T][N]
     StageD2* d_d2 = nullptr;      // [T] when all_d2
+    bool all_dk4 = false;         // every stage fits a complete depth-4 tree (and the model is not all_d2)
+    StageDK4* d_dk4 = nullptr;    // [T] when all_dk4
 };
 
 // ------------------------------------------------------------------------------------------------ profiling hooks
