@@ -170,3 +170,26 @@ def test_level_subset_plan_keeps_layout():
     assert sub.info.n_loc == sum(full.levels[k].win_rows * full.levels[k].win_cols for k in ids)
     none = plan_geometry(480, 640, OPTS, spec, 12, 12, level_ids=[])          # a rank that got no level
     assert none.info.n_loc == 0 and all(lv.skipped for lv in none.levels)
+
+
+def test_plan_geometry_property_random_sizes():
+    """level sizes must equal the reference's Python-double arithmetic (channels.py:124-131) for arbitrary frames:
+    a one-pixel difference in any level would shift every window of that level."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(8, 4500), st.integers(8, 4500), st.integers(1, 12), st.sampled_from([1, 2]))
+    def check(Hh, Ww, npo, shrink):
+        opts = dict(shrink=shrink, n_per_oct=npo, smooth=1, channels=wb.channels.grad_hist)
+        plan = plan_geometry(Hh, Ww, opts, wb.channels.resolve_channels(wb.channels.grad_hist), 12, 12)
+        k = 0
+        h, w = Hh, Ww
+        while not (w < 8 or h < 8):
+            for i in range(npo):
+                nh, nw = O.level_size(h, w, i, npo, shrink)
+                lv = plan.levels[k]
+                assert (lv.nh, lv.nw) == (nh, nw) and lv.scale == nw / Ww / shrink
+                k += 1
+            h, w = h // 2, w // 2
+        assert k == plan.n_levels
+    check()
