@@ -111,7 +111,7 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
             g->round_full = env_int("WBG_CAS_ROUND_FULL", 32);
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
-            g->pack = env_int("WBG_CAS_PACK", 0);
+            g->pack = env_int("WBG_CAS_PACK", -1);
             return true;
         }
     }

@@ -90,6 +90,9 @@ __device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.l
 __device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
 enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2 };
+#ifndef D2_DEPENDENT_MIN_NK
+#define D2_DEPENDENT_MIN_NK 2       // slots per thread from which the depth-2 path gathers only the taken child
+#endif
 
 template <int MODE, int NK, int WPT>
 __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&wa)[WPT], float (&hs)[WPT], float (&alive)[WPT],
@@ -138,28 +141,56 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
         for (int k = 0; k < NK; ++k) entered[k] = 0.f;
 #pragma unroll 4
         for (int s = t; s < t_end; ++s) {
+            // offsets, theta and thresholds are only ever used as uniform operands; the four leaves are selected
+            // between per lane and are read as one 16-byte constant load into vector registers
             const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
-            const int4 A = rec[0], B = rec[1], Cc = rec[2];
-            const float thr0 = __int_as_float(A.y), thr1 = __int_as_float(A.w), thr4 = __int_as_float(B.y);
-            const float p2 = __int_as_float(B.z), p3 = __int_as_float(B.w);
-            const float p5 = __int_as_float(Cc.x), p6 = __int_as_float(Cc.y), theta = __int_as_float(Cc.z);
-            float x0[NK], xa[NK], xb[NK];
+            const int4 A = rec[0], B = rec[1];
+            const float4 Lf = *reinterpret_cast<const float4*>(&c_d2[s].p2);
+            const float theta = __int_as_float(A.w);
+            const float thr0 = __int_as_float(B.x), thr1 = __int_as_float(B.y), thr4 = __int_as_float(B.z);
+            const float p2 = Lf.x, p3 = Lf.y, p5 = Lf.z, p6 = Lf.w;
+            if (NK >= D2_DEPENDENT_MIN_NK) {
+                // several slots per thread (the dense phases): the shared-memory pipe is the busiest unit there, so
+                // only the child that is actually taken is gathered -- 2 loads per window instead of 3; the latency of
+                // the dependent load hides behind the other slots and warps
+                float x0[NK], x1[NK];
+                bool l0[NK];
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                x0[k] = lds_f32(wa[k] + (unsigned)A.x);
-                xa[k] = lds_f32(wa[k] + (unsigned)A.z);
-                xb[k] = lds_f32(wa[k] + (unsigned)B.x);
-            }
+                for (int k = 0; k < NK; ++k) x0[k] = lds_f32(wa[k] + (unsigned)A.x);
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const float pa = (xa[k] <= thr1) ? p2 : p3;        // training.py:92 -- left iff X <= threshold
-                const float pb = (xb[k] <= thr4) ? p5 : p6;
-                const float m0 = fset_le(x0[k], thr0);
-                // m0 ? pa : pb on the FMA pipe, exact for finite leaves: (-m0*pb + pb) is pb or +0, then + m0*pa
-                const float pr = __fmaf_rn(m0, pa, __fmaf_rn(-m0, pb, pb));
-                entered[k] += alive[k];
-                hs[k] += pr;                                       // float32 accumulation in stage order (model.py:251)
-                alive[k] *= fset_ge(hs[k], theta);                 // model.py:255; theta = -inf passes every finite score
+                for (int k = 0; k < NK; ++k) {
+                    l0[k] = x0[k] <= thr0;                          // training.py:92 -- left iff X <= threshold
+                    x1[k] = lds_f32(wa[k] + (unsigned)(l0[k] ? A.y : A.z));
+                }
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const bool l1 = x1[k] <= (l0[k] ? thr1 : thr4);
+                    const float pl = l0[k] ? p2 : p5, pr_ = l0[k] ? p3 : p6;
+                    entered[k] += alive[k];
+                    hs[k] += l1 ? pl : pr_;                         // float32 accumulation in stage order (model.py:251)
+                    alive[k] *= fset_ge(hs[k], theta);              // model.py:255; theta = -inf passes every finite score
+                }
+            } else {
+                // one slot per thread (the sparse phases): latency matters, so both children are gathered speculatively
+                // and the three loads are independent of each other and of the previous stage
+                float x0[NK], xa[NK], xb[NK];
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    x0[k] = lds_f32(wa[k] + (unsigned)A.x);
+                    xa[k] = lds_f32(wa[k] + (unsigned)A.y);
+                    xb[k] = lds_f32(wa[k] + (unsigned)A.z);
+                }
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const float pa = (xa[k] <= thr1) ? p2 : p3;
+                    const float pb = (xb[k] <= thr4) ? p5 : p6;
+                    const float m0 = fset_le(x0[k], thr0);
+                    // m0 ? pa : pb on the FMA pipe, exact for finite leaves: (-m0*pb + pb) is pb or +0, then + m0*pa
+                    const float pr = __fmaf_rn(m0, pa, __fmaf_rn(-m0, pb, pb));
+                    entered[k] += alive[k];
+                    hs[k] += pr;
+                    alive[k] *= fset_ge(hs[k], theta);
+                }
             }
         }
 #pragma unroll
@@ -263,12 +294,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
 #pragma unroll
         for (int k = 0; k < WPT; ++k) mine |= alive[k] != 0.f;
         if (__any_sync(0xffffffffu, mine)) {
-            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*THREADS < n_slots (warp-uniform)
+            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*stride < n_slots (warp-uniform)
             const int first = warp << 5;
-            if (WPT >= 8 && first + 4 * stride < n_slots) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (first + 2 * stride < n_slots) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (first + stride < n_slots) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            const int kmax = first < stride ? (n_slots - first + stride - 1) / stride : 0;
+            if (WPT >= 8 && kmax > 4) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (kmax == 4) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (kmax == 3) run_round<MODE, 3, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (kmax == 2) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            else if (kmax == 1) run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
         }
         // ---- how many windows of the tile are still alive
         unsigned bal[WPT];
@@ -319,7 +352,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
         }
         __syncthreads();
         n_slots = n_alive;
-        if (p.pack > 0) stride = min(THREADS, ((n_slots + p.pack - 1) / p.pack + 31) & ~31);
+        // balanced layout: the fewest slots per thread that hold all survivors (pack < 0), or a fixed number, over as
+        // few warps as that takes -- every warp with slots then has the same amount of work in a round
+        {
+            const int per = p.pack < 0 ? (n_slots + THREADS - 1) / THREADS : p.pack;
+            if (per > 0) stride = min(THREADS, ((n_slots + per - 1) / per + 31) & ~31);
+        }
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const int idx = tid + k * stride;
@@ -543,6 +581,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
     p.pack = g.pack > g.wpt ? g.wpt : g.pack;
+    if (g.wpt > 4 && p.pack < 0) p.pack = 0;     // the automatic layout needs NK = per-thread slot count <= 4
     const int smem = g.smem_bytes;
     if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));

@@ -93,11 +93,10 @@ struct __align__(16) NodeDev {
 
 // One canonical depth-2 stage for the constant-memory fast path (48 bytes).
 struct __align__(16) StageD2 {
-    int off0; float thr0;          // root
-    int off1; float thr1;          // left child
-    int off4; float thr4;          // right child
-    float p2, p3, p5, p6;          // leaves LL, LR, RL, RR
-    float theta; float pad_;
+    int off0, off1, off4;          // byte offsets of the root / left child / right child feature in the planar patch
+    float theta;
+    float thr0, thr1, thr4, pad_;  // their thresholds
+    float p2, p3, p5, p6;          // leaves LL, LR, RL, RR (one 16-byte group: they go to vector registers)
 };
 constexpr int D2_MAX_STAGES = 1280;  // 61,440 bytes of __constant__
 
