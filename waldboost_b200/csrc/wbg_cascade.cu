@@ -39,6 +39,7 @@ struct CascadeParams {
     int C, m, n;
     int TR, TC, pitch, plane;
     int list_cap, compact_num, compact_den, round_full, round_mid, round_tail, pack;
+    int rec_off;             // byte offset of the staged stage records inside the dynamic shared memory (MODE_DK4)
     unsigned* mask;
     long long mask_stride;  // words per frame
     float* score;
@@ -73,6 +74,12 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+// 8-byte variant; volatile because the staged stage records it reads are rewritten every round
+__device__ __forceinline__ float2 lds_v2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 
 // One round (stages [t, t_end)) of the cascade for the first NK window slots of a thread; wa[k] is the shared-memory
 // byte address of the window's origin inside the staged patch.
@@ -90,6 +97,7 @@ __device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.l
 __device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
 enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2 };
+constexpr int DK4_ROUND_MAX = 64;   // stages per round of the depth-4 path: their records (12 KB) are staged in shared memory
 #ifndef D2_DEPENDENT_MIN_NK
 #define D2_DEPENDENT_MIN_NK 2       // slots per thread from which the depth-2 path gathers only the taken child
 #endif
@@ -100,33 +108,38 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
                                           const float* __restrict__ thetas, const StageDK4* __restrict__ dk4) {
     constexpr bool D2 = MODE == MODE_D2;
     if (MODE == MODE_DK4) {
-        // complete depth-4 stages in heap order: the root comes through the uniform path, levels 1..3 and the leaf are
-        // lane-dependent 8- / 4-byte reads of the 192-byte stage record (a handful of distinct addresses per warp,
-        // served by L1); every load is unconditional, so there is no divergence and the slots of a thread overlap.
+        // complete depth-4 stages in heap order.  The records of the round were staged in shared memory (rec_base): the
+        // root and theta are broadcast reads, levels 1..3 and the leaf are lane-dependent 8- / 4-byte reads with at
+        // most 2 / 4 / 8 / 16 distinct addresses per warp.  Every load is unconditional, so there is no divergence and
+        // the slots of a thread and the two unrolled stages overlap.
         float entered[NK];
 #pragma unroll
         for (int k = 0; k < NK; ++k) entered[k] = 0.f;
+        const unsigned rec_base = (unsigned)N;      // (argument reused) shared-window address of the first staged record
 #pragma unroll 2
         for (int s = t; s < t_end; ++s) {
-            const StageDK4* __restrict__ rec = dk4 + s;
-            const int2 root = __ldg(&rec->node[0]);
-            const float theta = __ldg(&rec->theta);
-            int idx[NK];
+            const unsigned rec = rec_base + (unsigned)(s - t) * (unsigned)sizeof(StageDK4);
+            const float2 root = lds_v2(rec);
+            const float theta = lds_f32(rec + 120u);
+            unsigned nd_addr[NK];                   // address of the current node record; node i sits at rec + 8 i
 #pragma unroll
-            for (int k = 0; k < NK; ++k) idx[k] = (lds_f32(wa[k] + (unsigned)root.x) <= __int_as_float(root.y)) ? 1 : 2;
+            for (int k = 0; k < NK; ++k)
+                nd_addr[k] = rec + ((lds_f32(wa[k] + (unsigned)__float_as_int(root.x)) <= root.y) ? 8u : 16u);
 #pragma unroll
             for (int lvl = 1; lvl < 4; ++lvl) {
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                    const int2 nd = __ldg(&rec->node[idx[k]]);
-                    idx[k] = 2 * idx[k] + ((lds_f32(wa[k] + (unsigned)nd.x) <= __int_as_float(nd.y)) ? 1 : 2);   // training.py:92
+                    const float2 nd = lds_v2(nd_addr[k]);
+                    // children of node i are 2i+1 / 2i+2: address rec + 8(2i+1) = 2*addr - rec + 8      (training.py:92)
+                    nd_addr[k] = 2u * nd_addr[k] - rec + ((lds_f32(wa[k] + (unsigned)__float_as_int(nd.x)) <= nd.y) ? 8u : 16u);
                 }
             }
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
                 entered[k] += alive[k];
-                hs[k] += __ldg(&rec->leaf[idx[k] - 15]);           // float32 accumulation in stage order (model.py:251)
-                alive[k] *= fset_ge(hs[k], theta);                 // model.py:255
+                // leaf j = i - 15 is the float at rec + 128 + 4 j, and nd_addr = rec + 8 i
+                hs[k] += lds_f32(rec + 128u + ((nd_addr[k] - rec) >> 1) - 60u);     // float32 accumulation in stage order (model.py:251)
+                alive[k] *= fset_ge(hs[k], theta);                                  // model.py:255
             }
         }
 #pragma unroll
@@ -285,11 +298,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
 
     // slot idx = tid + k*stride.  After a re-pack the survivors are laid out `p.pack` slots per thread over as few
     // warps as needed, so the per-stage record loads keep being shared by several windows of a thread.
+    // generic path: nodes per stage; depth-4 path: shared-window address of the staged stage records
+    const int aux = MODE == MODE_DK4 ? (int)((unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)p.rec_off) : p.N;
     int n_slots = nwin, n_alive = nwin, t = 0, round = 0, stride = THREADS;
     unsigned my_weak = 0;
     while (t < p.T && n_alive > 0) {
         // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
-        const int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
+        int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
+        if (MODE == MODE_DK4) {
+            // stage this round's stage records in shared memory (all readers of the previous round passed the barrier
+            // that ended it)
+            t_end = min(t_end, t + DK4_ROUND_MAX);
+            const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t);
+            int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
+            for (int i = tid; i < (t_end - t) * (int)(sizeof(StageDK4) / 16); i += THREADS) d[i] = __ldg(g + i);
+            __syncthreads();
+        }
         bool mine = false;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) mine |= alive[k] != 0.f;
@@ -297,11 +321,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 
             // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*stride < n_slots (warp-uniform)
             const int first = warp << 5;
             const int kmax = first < stride ? (n_slots - first + stride - 1) / stride : 0;
-            if (WPT >= 8 && kmax > 4) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (kmax == 4) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (kmax == 3) run_round<MODE, 3, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (kmax == 2) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
-            else if (kmax == 1) run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, p.N, p.theta, p.dk4);
+            if (WPT >= 8 && kmax > 4) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
+            else if (kmax == 4) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
+            else if (kmax == 3) run_round<MODE, 3, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
+            else if (kmax == 2) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
+            else if (kmax == 1) run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
         }
         // ---- how many windows of the tile are still alive
         unsigned bal[WPT];
@@ -582,7 +606,9 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
     p.pack = g.pack > g.wpt ? g.wpt : g.pack;
     if (g.wpt > 4 && p.pack < 0) p.pack = 0;     // the automatic layout needs NK = per-thread slot count <= 4
-    const int smem = g.smem_bytes;
+    const bool use_dk4 = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
+    p.rec_off = (g.smem_bytes + 15) & ~15;
+    const int smem = use_dk4 ? p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4) : g.smem_bytes;
     if (model->all_d2)
         WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
 #define WBG_CAS_LAUNCH(MODEV, TH, WP)                                                                                        \
@@ -594,7 +620,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
 #define WBG_CAS_LAUNCH_MODE(TH, WP)                                                       \
     do {                                                                                  \
         if (model->all_d2) WBG_CAS_LAUNCH(MODE_D2, TH, WP);                               \
-        else if (model->all_dk4 && !getenv("WBG_CAS_GENERIC")) WBG_CAS_LAUNCH(MODE_DK4, TH, WP); \
+        else if (use_dk4) WBG_CAS_LAUNCH(MODE_DK4, TH, WP);                               \
         else WBG_CAS_LAUNCH(MODE_GENERIC, TH, WP);                                        \
     } while (0)
     if (g.threads == 512 && g.wpt == 8) {
