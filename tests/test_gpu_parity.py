@@ -506,3 +506,42 @@ def test_fpga_channels_direct_detect_and_errors(tmp_path):
     assert M2.channel_opts["channels"] is wb.fpga.grad_hist_4_u1
     with pytest.raises(Exception):                         # float32 frames are rejected for the integer channels
         M.detect(img.astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_shapes_and_options_vs_oracle(seed):
+    """seeded sweep over frame sizes (odd, tiny, wide), dtypes, channel options, window shapes and tree depths: the
+    whole detect() against the oracle -- exercises partial tiles, levels smaller than a tile or than the window, the
+    scalar and the vectorised octave chain, every level kernel variant and all three cascade paths."""
+    rng = np.random.default_rng(100 + seed)
+    Hh, Ww = int(rng.integers(24, 260)), int(rng.integers(24, 330))
+    if seed % 4 == 0:
+        Ww = (Ww // 16 + 1) * 16                     # 8-byte aligned rows: vectorised octave chain
+        Hh = (Hh // 2 + 1) * 2
+    dtype = np.float32 if seed % 3 == 2 else np.uint8
+    frame = S.synthetic_frame(2000 + seed, Hh, Ww) if seed % 2 else S.noise_frame(2000 + seed, Hh, Ww)
+    frame = frame.astype(dtype)
+    if dtype == np.float32:
+        frame = frame + rng.random(frame.shape).astype(np.float32)
+    fn = [CH.grad_hist, functools.partial(CH.grad_hist, n_bins=6), CH.grad_mag, CH.grad_mag_hist,
+          functools.partial(CH.grad_mag, norm=3)][seed % 5]
+    opts = dict(shrink=int(rng.integers(1, 3)), n_per_oct=int(rng.integers(1, 6)), smooth=int(rng.integers(0, 2)), channels=fn)
+    C_ = wb.channels.channel_count(wb.channels.resolve_channels(fn))
+    m, n = int(rng.integers(3, 15)), int(rng.integers(3, 15))
+    depth = int(rng.integers(1, 6))
+    try:
+        M = make_model((m, n, C_), opts, int(rng.integers(4, 30)), depth, frame, seed=seed, keep_total=float(rng.choice([1e-2, 0.2])))
+    except (ValueError, IndexError):
+        pytest.skip("frame too small for a calibration level")
+    Cs = oracle_cascade(M)
+    got = list(M.channels(frame))
+    ref = list(Cs.channels(frame))
+    assert_pyramid_close(got, ref)
+    dt = M.detect(frame)
+    boxes, scores, _ = Cs.detect(frame)
+    exact_channels = all(np.array_equal(a, b) for (a, _), (b, _) in zip(got, ref))
+    if exact_channels:
+        assert np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
+        assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak)
+    else:                                            # float32 frames / grad_mag: channels within 1e-5, hits may flip at a threshold
+        assert M.n_loc == Cs.n_loc and abs(len(dt) - scores.size) <= max(2, 0.05 * scores.size)
