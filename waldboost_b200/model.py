@@ -222,10 +222,15 @@ class Model:
             raise ValueError("detect_batch takes [B,H,W] frames")
         hits, counts, _, _ = self._run(np.ascontiguousarray(images), levels=levels)
         per_frame = counts.sum(axis=1) if counts.size else np.zeros(images.shape[0], np.int64)
+        # one (N,4) box array and one score array for the whole batch; the per-frame Boxes are views into them
+        all_boxes = np.stack([hits["x1"], hits["y1"], hits["x2"], hits["y2"]], axis=1) if hits.size else np.empty((0, 4), np.float32)
+        all_scores = np.ascontiguousarray(hits["score"]) if hits.size else np.empty(0, np.float32)
         out, pos = [], 0
         for b in range(images.shape[0]):
             k = int(per_frame[b])
-            out.append(self._boxes_from_hits(hits[pos:pos + k]))
+            boxes = Boxes(all_boxes[pos:pos + k])
+            boxes.set_field("scores", all_scores[pos:pos + k])
+            out.append(boxes)
             pos += k
         return (out, hits) if return_hits else out
 
