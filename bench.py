@@ -49,15 +49,13 @@ def _cpu_worker(job):
     seed, levels, profile, h, w = job
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import wb_oracle as O  # noqa: F401  (checker / CPU baseline only)
+    import wb_oracle as O  # (checker / CPU baseline only)
     import waldboost_b200 as wb
-    from helpers import oracle_cascade
     from waldboost_b200 import synthetic as S
-    M = wb.Model.load(MODEL_B)
+    M = wb.Model.load(MODEL_B)              # host-side .pb parsing only; no GPU is touched in the worker
     if profile == "dense":
         M.theta = [-np.inf] * len(M)
-    Cs = oracle_cascade(M)
+    Cs = O.cascade_from_model(M)
     frame = S.synthetic_frame(seed, h, w)
     t0 = time.perf_counter()
     hits = Cs.detect(frame, levels)[1].size

@@ -448,3 +448,29 @@ def gather_samples(chns, rs, cs, shape):
     if rs.size == 0:
         return np.empty((0,) + tuple(shape), dtype=chns.dtype)
     return np.array([chns[r:r + m, c:c + n, ...] for r, c in zip(rs, cs)])
+
+
+# =============================================================================================== test glue
+def oracle_channel_fn(fn):
+    """Map a product channel function (waldboost_b200.channels.* / waldboost_b200.fpga.*, possibly wrapped in
+    functools.partial with keyword arguments) to the oracle function of the same name.  Name based, so that this
+    module never imports the product package."""
+    import functools
+    kw = {}
+    base = fn
+    while isinstance(base, functools.partial):
+        kw = {**base.keywords, **kw}
+        base = base.func
+    table = {"grad_hist": grad_hist, "grad_mag": grad_mag, "grad_mag_hist": grad_mag_hist,
+             "grad_hist_4_u1": grad_hist_4_u1, "grad_mag_u1": grad_mag_u1}
+    target = table[base.__name__]
+    return functools.partial(target, **kw) if kw else target
+
+
+def cascade_from_model(model):
+    """product Model (duck typed: shape, channel_opts, classifier with DTree arrays, theta) -> oracle Cascade."""
+    opts = dict(model.channel_opts, channels=oracle_channel_fn(model.channel_opts["channels"])) if model.channel_opts else None
+    Cs = Cascade(model.shape, opts)
+    for w, th in zip(model.classifier, model.theta):
+        Cs.append(DTree([tuple(f) for f in w.feature], w.threshold, w.left, w.right, w.prediction), th)
+    return Cs

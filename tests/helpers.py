@@ -9,33 +9,14 @@ from waldboost_b200 import synthetic as S
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-ORACLE_FN = {"grad_hist": O.grad_hist, "grad_mag": O.grad_mag, "grad_mag_hist": O.grad_mag_hist,
-             "grad_hist_4_u1": O.grad_hist_4_u1, "grad_mag_u1": O.grad_mag_u1}
-
-
 def oracle_opts(channel_opts):
-    """product channel_opts (functions of waldboost_b200.channels, maybe partial) -> oracle channel_opts."""
-    import functools
-    from waldboost_b200.channels import resolve_channels
-    spec = resolve_channels(channel_opts["channels"])
-    kind = spec["name"]
-    if kind in ("grad_hist_4_u1", "grad_mag_u1"):
-        return dict(channel_opts, channels=ORACLE_FN[kind])
-    if kind == "grad_hist":
-        fn = functools.partial(O.grad_hist, n_bins=spec["n_bins"], full=spec["full"], bias=spec["bias"])
-    elif kind == "grad_mag":
-        fn = functools.partial(O.grad_mag, norm=spec["norm"], eps=spec["eps"])
-    else:
-        fn = functools.partial(O.grad_mag_hist, n_bins=spec["n_bins"], norm=spec["norm"], eps=spec["eps"])
-    return dict(channel_opts, channels=fn)
+    """product channel_opts (functions of waldboost_b200.channels / .fpga, maybe partial) -> oracle channel_opts."""
+    return dict(channel_opts, channels=O.oracle_channel_fn(channel_opts["channels"]))
 
 
 def oracle_cascade(model):
     """wb.Model -> oracle Cascade with identical arrays."""
-    Cs = O.Cascade(model.shape, oracle_opts(model.channel_opts) if model.channel_opts else None)
-    for w, th in model:
-        Cs.append(O.DTree([tuple(f) for f in w.feature], w.threshold, w.left, w.right, w.prediction), th)
-    return Cs
+    return O.cascade_from_model(model)
 
 
 def make_model(shape, channel_opts, n_stages, depth, frame, seed=7, keep_total=None, calib_levels=1):
