@@ -10,7 +10,10 @@
  *   - plain pointers and sizes only; no CUDA or torch types (a stream is passed as `void*` = cudaStream_t).
  *   - the CALLER owns every image / channel / hit / workspace buffer (device memory unless the name ends in
  *     `_host`); the library owns only the opaque handles and their small device-side parameter tables.
- *   - every compute entry point is asynchronous and ordered on `stream`; none of them synchronises.
+ *   - every compute entry point is asynchronous and ordered on `stream`; none of them synchronises, with one
+ *     exception: the depth-2 stage table of a cascade lives in the device's constant bank, and wbg_cascade_scan /
+ *     wbg_predict_on_image drain the device and load it synchronously when a DIFFERENT model used the bank last
+ *     (first use, or alternating between models).
  *   - return value 0 = WBG_OK, negative = error; `wbg_last_error()` returns a thread-local message.
  *   - handles are bound to the CUDA device that was current at creation and are not thread-safe, like the
  *     reference's Model whose stats counters make predict_on_image non-reentrant (model.py:248,252).
@@ -187,7 +190,7 @@ int wbg_gather_samples(const float* X, int32_t u, int32_t v, int32_t c, const in
 /* ---- measurement aid (bench.py): while enabled, the library brackets its two dominant kernels -- the fused
  * per-level channel kernel and the cascade kernel -- with CUDA events on the caller's stream.  wbg_profile_read
  * waits for the recorded events, returns the accumulated kernel time (ms) and launch count per kind since the last
- * read, and clears them.  Not thread-safe; meant for one stream. */
+ * read, and clears them.  Safe to call from several host threads; a begin/end pair belongs to the launching thread. */
 enum { WBG_PROF_LEVEL_KERNEL = 0, WBG_PROF_CASCADE_KERNEL = 1, WBG_PROF_KINDS = 2 };
 int wbg_profile_enable(int32_t on);
 int wbg_profile_read(double* ms /* [WBG_PROF_KINDS] */, int64_t* launches /* [WBG_PROF_KINDS] */);

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
 #include <new>
 
 #include "wbg_internal.h"
@@ -33,12 +35,13 @@ extern "C" int wbg_device_count(void) {
 
 // ------------------------------------------------------------------------------------------------ profiling hooks
 struct ProfSpan { int kind; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mutex;                       // guards the two containers below
 static std::vector<ProfSpan> g_prof_spans;
-static cudaEvent_t g_prof_open[WBG_PROF_KINDS];
+static thread_local cudaEvent_t g_prof_open[WBG_PROF_KINDS];   // begin/end pairs are issued by one host thread
 
 void wbg_prof_begin(int kind, cudaStream_t stream) {
-    if (!g_prof_on) return;
+    if (!g_prof_on.load()) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, stream);
@@ -46,22 +49,26 @@ void wbg_prof_begin(int kind, cudaStream_t stream) {
 }
 
 void wbg_prof_end(int kind, cudaStream_t stream) {
-    if (!g_prof_on || !g_prof_open[kind]) return;
+    if (!g_prof_on.load() || !g_prof_open[kind]) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, stream);
-    g_prof_spans.push_back({kind, g_prof_open[kind], e});
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        g_prof_spans.push_back({kind, g_prof_open[kind], e});
+    }
     g_prof_open[kind] = nullptr;
 }
 
 extern "C" int wbg_profile_enable(int32_t on) {
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
     return WBG_OK;
 }
 
 extern "C" int wbg_profile_read(double* ms, int64_t* launches) {
     WBG_REQUIRE(ms && launches, "wbg_profile_read: null argument");
     for (int k = 0; k < WBG_PROF_KINDS; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& s : g_prof_spans) {
         float t = 0.f;
         WBG_CUDA_TRY(cudaEventSynchronize(s.b));
@@ -425,6 +432,10 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
 
     wbg_model* m = new (std::nothrow) wbg_model();
     if (!m) { wbg_set_error("out of host memory"); return WBG_ENOMEM; }
+    {
+        static std::atomic<unsigned long long> next_uid{1};
+        m->uid = next_uid.fetch_add(1);
+    }
     m->m = d->win_m; m->n = d->win_n; m->C = d->channels; m->T = T; m->N = N; m->geom = g; m->all_d2 = all_d2; m->all_dk4 = all_dk4;
     cudaError_t e = cudaGetDevice(&m->device);
     if (e == cudaSuccess && T > 0) {

@@ -23,6 +23,8 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "wbg_internal.h"
 
 __constant__ StageD2 c_d2[D2_MAX_STAGES];
@@ -609,8 +611,20 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const bool use_dk4 = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
     p.rec_off = (g.smem_bytes + 15) & ~15;
     const int smem = use_dk4 ? p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4) : g.smem_bytes;
-    if (model->all_d2)
-        WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
+    if (model->all_d2) {
+        // The depth-2 stage table lives in the constant bank, which is one per device.  It is (re)loaded only when
+        // another model owned it: first every kernel that may still read the old table is drained, then the copy is
+        // done synchronously, so launches of the same model on any number of streams never race with a copy.
+        static std::mutex mtx;
+        static unsigned long long owner[64] = {0};
+        std::lock_guard<std::mutex> lock(mtx);
+        const int dev = model->device >= 0 && model->device < 64 ? model->device : 0;
+        if (owner[dev] != model->uid) {
+            WBG_CUDA_TRY(cudaDeviceSynchronize());
+            WBG_CUDA_TRY(cudaMemcpyToSymbol(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice));
+            owner[dev] = model->uid;
+        }
+    }
 #define WBG_CAS_LAUNCH(MODEV, TH, WP)                                                                                        \
     do {                                                                                                                     \
         WBG_CUDA_TRY(cudaFuncSetAttribute(cascade_kernel<MODEV, TH, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \

@@ -112,6 +112,7 @@ struct __align__(16) StageDK4 {
 static_assert(sizeof(StageDK4) == 192, "StageDK4 layout");
 
 struct wbg_model {
+    unsigned long long uid = 0;   // unique per created model (never reused): identifies the owner of the constant bank
     int m = 0, n = 0, C = 0, T = 0, N = 0;
     CascadeGeom geom{};
     int device = -1;
