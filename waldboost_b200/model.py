@@ -100,13 +100,14 @@ class Model:
 
     def _device_model(self):
         """The lists are user-mutable (reference scripts assign model.theta, append stages): re-sync lazily."""
-        key = (tuple(int(x) for x in self.shape), tuple(id(w) for w in self.classifier),
+        eng = get_engine()
+        key = (eng.device.index, tuple(int(x) for x in self.shape), tuple(id(w) for w in self.classifier),
                tuple(float(t) for t in self.theta))
         if self._handle is None or key != self._handle_key:
             if len(self.classifier) != len(self.theta):
                 raise ValueError("classifier and theta must have the same length")
-            get_engine()
-            self._handle = ModelHandle(self.shape, self.classifier, self.theta)
+            with eng.torch.cuda.device(eng.device):        # the handle's tables live on the engine's device
+                self._handle = ModelHandle(self.shape, self.classifier, self.theta)
             self._handle_key = key
         return self._handle
 
