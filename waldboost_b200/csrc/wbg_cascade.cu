@@ -154,7 +154,11 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
         float entered[NK];              // stages the slot entered alive in this round (model.py:252)
 #pragma unroll
         for (int k = 0; k < NK; ++k) entered[k] = 0.f;
-#pragma unroll 4
+#ifndef D2_UNROLL
+#define D2_UNROLL 8
+#endif
+        constexpr int kD2Unroll = D2_UNROLL;
+#pragma unroll kD2Unroll
         for (int s = t; s < t_end; ++s) {
             // offsets, theta and thresholds are only ever used as uniform operands; the four leaves are selected
             // between per lane and are read as one 16-byte constant load into vector registers
