@@ -118,7 +118,11 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 #pragma unroll
         for (int k = 0; k < NK; ++k) entered[k] = 0.f;
         const unsigned rec_base = (unsigned)N;      // (argument reused) shared-window address of the first staged record
-#pragma unroll 2
+#ifndef DK4_UNROLL
+#define DK4_UNROLL 2
+#endif
+        constexpr int kDk4Unroll = DK4_UNROLL;
+#pragma unroll kDk4Unroll
         for (int s = t; s < t_end; ++s) {
             const unsigned rec = rec_base + (unsigned)(s - t) * (unsigned)sizeof(StageDK4);
             const float2 root = lds_v2(rec);
