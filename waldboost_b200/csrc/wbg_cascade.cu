@@ -244,7 +244,10 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 }
 
 template <int MODE, int THREADS, int WPT>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : 3)) cascade_kernel(const CascadeParams p) {
+#ifndef CAS_MINB_512x4
+#define CAS_MINB_512x4 3
+#endif
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : CAS_MINB_512x4)) cascade_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int ENTRIES = WPT * WARPS;          // (slot, warp) ballot counts, a multiple of 32
     constexpr int EPL = ENTRIES / 32;             // entries scanned per lane of warp 0
