@@ -9,6 +9,8 @@
 #include <mutex>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around the two halves of detect() for nsys / ncu timelines
+
 #include "wbg_internal.h"
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -310,7 +312,10 @@ extern "C" int wbg_channel_pyramid(const wbg_plan* plan, const void* img, int32_
     WBG_REQUIRE(img && chns && workspace, "wbg_channel_pyramid: null buffer");
     WBG_REQUIRE(workspace_bytes >= wbg_pyramid_workspace_bytes(plan, dtype, batch), "wbg_channel_pyramid: workspace too small");
     WBG_REQUIRE(((uintptr_t)chns & 15) == 0 && ((uintptr_t)workspace & 255) == 0, "wbg_channel_pyramid: chns must be 16-byte and workspace 256-byte aligned");
-    return wbg_launch_pyramid(plan, img, dtype, batch, chns, workspace, workspace_bytes, (cudaStream_t)stream);
+    nvtxRangePushA("wbg_channel_pyramid");
+    const int rc = wbg_launch_pyramid(plan, img, dtype, batch, chns, workspace, workspace_bytes, (cudaStream_t)stream);
+    nvtxRangePop();
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ model
@@ -489,9 +494,12 @@ extern "C" int wbg_cascade_scan(const wbg_model* model, const wbg_plan* plan, co
     WBG_REQUIRE(plan->win_m == model->m && plan->win_n == model->n, "wbg_cascade_scan: plan window %dx%d != model window %dx%d",
                 plan->win_m, plan->win_n, model->m, model->n);
     WBG_REQUIRE(workspace_bytes >= wbg_cascade_workspace_bytes(plan, batch), "wbg_cascade_scan: workspace too small");
-    return wbg_launch_cascade(model, plan->d_levels, (int)plan->levels.size(), plan->ctiles, plan->chn_floats, plan->windows,
-                              chns, batch, hits, hit_cap, level_counts, (unsigned long long*)stats, (long long*)n_hits,
-                              workspace, workspace_bytes, (cudaStream_t)stream);
+    nvtxRangePushA("wbg_cascade_scan");
+    rc = wbg_launch_cascade(model, plan->d_levels, (int)plan->levels.size(), plan->ctiles, plan->chn_floats, plan->windows,
+                            chns, batch, hits, hit_cap, level_counts, (unsigned long long*)stats, (long long*)n_hits,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+    nvtxRangePop();
+    return rc;
 }
 
 // single channel map: a one-level table is written into the head of the workspace

@@ -332,7 +332,9 @@ class Engine:
         if not hasattr(self, "_pipe_streams"):
             self._pipe_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         cur = torch.cuda.current_stream(self.device)
-        spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
+        # a short first chunk gets the kernels going while the rest of the batch is still being copied
+        first = max(1, chunk // 4)
+        spans = [(0, first)] + [(lo, min(lo + chunk, B)) for lo in range(first, B, chunk)]
         jobs = []
         for i, (lo, hi) in enumerate(spans):
             slot = str(i & 1)
