@@ -545,3 +545,25 @@ def test_randomised_shapes_and_options_vs_oracle(seed):
         assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak)
     else:                                            # float32 frames / grad_mag: channels within 1e-5, hits may flip at a threshold
         assert M.n_loc == Cs.n_loc and abs(len(dt) - scores.size) <= max(2, 0.05 * scores.size)
+
+
+def test_detect_input_edge_cases():
+    """frames below the octave cut-off, non-contiguous views, unsupported dtypes (reference channels.py:93-108)."""
+    frame = S.synthetic_frame(1000, 96, 128)
+    M = make_model((12, 12, 4), OPTS_A, 8, 2, frame, keep_total=0.2)
+    dt = M.detect(np.zeros((7, 100), np.uint8))                     # w < 8 or h < 8: no octave, no level, no box
+    assert len(dt) == 0 and dt.has_field("scores") and list(M.channels(np.zeros((7, 100), np.uint8))) == []
+    big = S.synthetic_frame(1000, 192, 256)
+    view = big[::2, ::2]                                            # strided view of a larger array
+    a, b = M.detect(view), M.detect(np.ascontiguousarray(view))
+    assert np.array_equal(a.get(), b.get()) and np.array_equal(a.get_field("scores"), b.get_field("scores"))
+    with pytest.raises(TypeError):
+        M.detect(frame.astype(np.int32))
+    with pytest.raises(TypeError):
+        M.detect(frame.tolist())
+    with pytest.raises(ValueError):
+        M.detect(frame[None])
+    out = M.detect_batch([frame, frame])                            # list of frames
+    assert len(out) == 2 and np.array_equal(out[0].get(), out[1].get())
+    with pytest.raises(ValueError):
+        M.detect_batch(np.zeros((96, 128), np.uint8))
