@@ -337,6 +337,9 @@ def run_gpu(args):
                 "traffic": (traffic[name]["bytes_per_frame"] * B) if name in traffic else None,
                 "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
                 "ms_per_launch": per_launch_s * 1e3, "peak_source": peak_src,
+                # context from the committed ncu capture (profiles/r01_ncu_full_final.csv), not measured in this run:
+                # both kernels are bound by instruction issue, not by HBM
+                "ncu": {k: v for k, v in traffic.get(name, {}).items() if k.startswith("ncu_")} or None,
                 "share_of_step": ms / n / (ms_total / args.steps)}
 
     r_pyr = roof("level_kernel", pyr_b, "level_kernel")
