@@ -10,10 +10,10 @@
  *   - plain pointers and sizes only; no CUDA or torch types (a stream is passed as `void*` = cudaStream_t).
  *   - the CALLER owns every image / channel / hit / workspace buffer (device memory unless the name ends in
  *     `_host`); the library owns only the opaque handles and their small device-side parameter tables.
- *   - every compute entry point is asynchronous and ordered on `stream`; none of them synchronises, with one
- *     exception: the depth-2 stage table of a cascade lives in the device's constant bank, and wbg_cascade_scan /
- *     wbg_predict_on_image drain the device and load it synchronously when a DIFFERENT model used the bank last
- *     (first use, or alternating between models).
+ *   - every compute entry point is asynchronous and ordered on `stream`; none of them waits on the host.  The
+ *     depth-2 stage table of a cascade lives in the device's constant bank; when a DIFFERENT model used the bank last
+ *     (first use, or alternating between models) wbg_cascade_scan / wbg_predict_on_image enqueue the table copy on
+ *     `stream` behind CUDA events of the earlier cascade launches on other streams -- device-side ordering only.
  *   - return value 0 = WBG_OK, negative = error; `wbg_last_error()` returns a thread-local message.
  *   - handles are bound to the CUDA device that was current at creation and are not thread-safe, like the
  *     reference's Model whose stats counters make predict_on_image non-reentrant (model.py:248,252).
@@ -194,6 +194,16 @@ int wbg_gather_samples(const float* X, int32_t u, int32_t v, int32_t c, const in
 enum { WBG_PROF_LEVEL_KERNEL = 0, WBG_PROF_CASCADE_KERNEL = 1, WBG_PROF_KINDS = 2 };
 int wbg_profile_enable(int32_t on);
 int wbg_profile_read(double* ms /* [WBG_PROF_KINDS] */, int64_t* launches /* [WBG_PROF_KINDS] */);
+
+/* ---- instrumentation of the cascade kernel (profiles/): while enabled, every cascade launch on the current device
+ * adds to 16 device-side uint64 counters; enable(1) zeroes them.  The reference has no counterpart beyond
+ * n_loc / n_weak (model.py:69-89); these counters split the kernel's work the same way:
+ *   [0..3] executed slot-stages (32 lanes x stages of every warp-round) with 1 / 2 / 3 / 4 window slots per thread
+ *   [4]    live slot-stages = windows entering a stage = n_weak (model.py:252)
+ *   [5]    rounds summed over tiles      [6] survivors written to the shared-memory pool      [7] tiles
+ *   [8..15] reserved */
+int wbg_cascade_counters_enable(int32_t on);
+int wbg_cascade_counters_read(uint64_t* out16);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,8 @@ SYMBOLS = {
     "wbg_gather_samples": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P, _P]),
     "wbg_profile_enable": (C.c_int, [_I32]),
     "wbg_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "wbg_cascade_counters_enable": (C.c_int, [_I32]),
+    "wbg_cascade_counters_read": (C.c_int, [C.POINTER(C.c_uint64)]),
 }
 PROF_KINDS = ("level_kernel", "cascade_kernel")
 

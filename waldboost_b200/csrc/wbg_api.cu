@@ -96,7 +96,7 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
     // A larger tile keeps the lanes of the sparse late stages fuller and halves the halo overhead, but fewer
     // resident CTAs hide less of each tile's barrier and tail latency.
     struct Cand { int TR, TC, threads, wpt, budget; };
-    const Cand cand[] = {{32, 64, 512, 4, 74 * 1024}, {32, 128, 512, 8, 112 * 1024}, {32, 32, 256, 4, 44 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
+    const Cand cand[] = {{32, 64, 512, 4, 74 * 1024}, {32, 32, 256, 4, 44 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
@@ -109,8 +109,8 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
         int pitch = c.TC + n - 1;
         pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are re-packed
         const long long plane = (long long)rows * pitch;
-        // the re-pack lists hold at most the survivors of a re-pack: slots * num / den
-        const int list_cap = (int)(((long long)c.threads * c.wpt * cnum + cden - 1) / cden);
+        // the survivor pool can hold every window of the tile (a round in which nothing is rejected)
+        const int list_cap = c.threads * c.wpt;
         const long long bytes = plane * C * 4 + (long long)list_cap * (4 + 2) + 256;
         if (bytes <= c.budget && plane < 65536) {
             g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
@@ -120,7 +120,11 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
             g->round_full = env_int("WBG_CAS_ROUND_FULL", 32);
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
-            g->pack = env_int("WBG_CAS_PACK", -1);
+            g->round_n1 = env_int("WBG_CAS_ROUND_N1", c.threads);
+            g->round_n2 = env_int("WBG_CAS_ROUND_N2", 64);
+            g->pack = env_int("WBG_CAS_PACK", 1);
+            g->sm_maxnk = env_int("WBG_CAS_SM_MAXNK", 2);
+            g->spec_n = env_int("WBG_CAS_SPEC_N", 128);
             return true;
         }
     }
@@ -329,7 +333,7 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 extern "C" void wbg_model_destroy(wbg_model* m) {
     if (!m) return;
     cudaFree(m->d_feature); cudaFree(m->d_threshold); cudaFree(m->d_left); cudaFree(m->d_right);
-    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_dk4);
+    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_d2s); cudaFree(m->d_dk4);
     delete m;
 }
 
@@ -453,6 +457,17 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
         if (e == cudaSuccess) e = upload(&m->d_theta, d->theta, (size_t)T);
         if (e == cudaSuccess) e = upload(&m->d_nodes, nodes.data(), TN);
         if (e == cudaSuccess && all_d2) e = upload(&m->d_d2, d2.data(), (size_t)T);
+        if (e == cudaSuccess && all_d2) {
+            std::vector<StageD2S> d2s((size_t)T);
+            for (int t = 0; t < T; ++t) {
+                const StageD2& a = d2[t];
+                StageD2S& b = d2s[t];
+                b.off0 = a.off0; b.thr0 = a.thr0; b.theta = a.theta; b.pad_ = 0.f;
+                b.offL = a.off1; b.thrL = a.thr1; b.pLL = a.p2; b.pLR = a.p3;
+                b.offR = a.off4; b.thrR = a.thr4; b.pRL = a.p5; b.pRR = a.p6;
+            }
+            e = upload(&m->d_d2s, d2s.data(), (size_t)T);
+        }
         if (e == cudaSuccess && all_dk4) e = upload(&m->d_dk4, dk4.data(), (size_t)T);
     }
     if (e != cudaSuccess) {
