@@ -122,9 +122,7 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
             g->round_n1 = env_int("WBG_CAS_ROUND_N1", c.threads);
             g->round_n2 = env_int("WBG_CAS_ROUND_N2", 64);
-            g->pack = env_int("WBG_CAS_PACK", 1);
-            g->sm_maxnk = env_int("WBG_CAS_SM_MAXNK", 2);
-            g->spec_n = env_int("WBG_CAS_SPEC_N", 128);
+            g->pack = env_int("WBG_CAS_PACK", 2);
             return true;
         }
     }
@@ -333,7 +331,7 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 extern "C" void wbg_model_destroy(wbg_model* m) {
     if (!m) return;
     cudaFree(m->d_feature); cudaFree(m->d_threshold); cudaFree(m->d_left); cudaFree(m->d_right);
-    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_d2s); cudaFree(m->d_dk4);
+    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_dk4);
     delete m;
 }
 
@@ -457,17 +455,6 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
         if (e == cudaSuccess) e = upload(&m->d_theta, d->theta, (size_t)T);
         if (e == cudaSuccess) e = upload(&m->d_nodes, nodes.data(), TN);
         if (e == cudaSuccess && all_d2) e = upload(&m->d_d2, d2.data(), (size_t)T);
-        if (e == cudaSuccess && all_d2) {
-            std::vector<StageD2S> d2s((size_t)T);
-            for (int t = 0; t < T; ++t) {
-                const StageD2& a = d2[t];
-                StageD2S& b = d2s[t];
-                b.off0 = a.off0; b.thr0 = a.thr0; b.theta = a.theta; b.pad_ = 0.f;
-                b.offL = a.off1; b.thrL = a.thr1; b.pLL = a.p2; b.pLR = a.p3;
-                b.offR = a.off4; b.thrR = a.thr4; b.pRL = a.p5; b.pRR = a.p6;
-            }
-            e = upload(&m->d_d2s, d2s.data(), (size_t)T);
-        }
         if (e == cudaSuccess && all_dk4) e = upload(&m->d_dk4, dk4.data(), (size_t)T);
     }
     if (e != cudaSuccess) {

@@ -41,9 +41,6 @@ struct CascadeParams {
     int n_levels, tiles_per_frame;
     const NodeDev* nodes;
     const StageDK4* dk4;
-    const StageD2S* d2s;     // depth-2 stages in the layout that is staged in shared memory per round
-    int sm_maxnk;            // rounds with at most this many window slots per thread read the staged records
-    int spec_n;              // pool kernel: speculative rounds (leaf bits, then accumulation) once at most this many windows are left
     const float* theta;
     int N, T;
     int C, m, n;
@@ -253,300 +250,9 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
     }
 }
 
-template <int MODE, int THREADS, int WPT>
 #ifndef CAS_MINB_512x4
 #define CAS_MINB_512x4 3
 #endif
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : (WPT == 8 ? 2 : CAS_MINB_512x4)) cascade_kernel(const CascadeParams p) {
-    constexpr int WARPS = THREADS / 32;
-    constexpr int ENTRIES = WPT * WARPS;          // (slot, warp) ballot counts, a multiple of 32
-    constexpr int EPL = ENTRIES / 32;             // entries scanned per lane of warp 0
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tile = reinterpret_cast<float*>(smem_raw);
-    float* s_score = tile + ((p.C * p.plane + 3) & ~3);
-    unsigned short* s_woff = reinterpret_cast<unsigned short*>(s_score + p.list_cap);
-    __shared__ int s_tot[ENTRIES];                // survivors per (slot, warp); stays 0 for retired warps
-    __shared__ int s_pre[ENTRIES];                // exclusive prefix of s_tot in slot-major order
-    __shared__ int s_cnt[3];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.x / p.tiles_per_frame;
-    const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
-    const int lvl = find_level_by_ctile(p.levels, p.n_levels, tile_id);
-    const LevelDev* __restrict__ L = p.levels + lvl;
-    const int v = L->v, win_rows = L->win_rows, win_cols = L->win_cols, ctiles_x = L->ctiles_x;
-    const long long chn_off = L->chn_off, win_off = L->win_off;
-    const int local = tile_id - L->ctile0;
-    const int ty = local / ctiles_x, tx = local - ty * ctiles_x;
-    const int r0 = ty * p.TR, c0 = tx * p.TC;
-    const int rows_valid = min(p.TR, win_rows - r0), cols_valid = min(p.TC, win_cols - c0);
-    const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;
-    const int pitch = p.pitch, plane = p.plane;
-    if (tid < 3) s_cnt[tid] = 0;
-
-    // ---- stage the channel patch, HWC in HBM -> planar in shared memory
-    const float* __restrict__ src = p.chns + (long long)frame * p.chn_stride + chn_off + ((long long)r0 * v + c0) * p.C;
-    if (p.C == 4) {
-        for (int i = tid; i < lrows * lcols; i += THREADS) {
-            const int rr = i / lcols, cc = i - rr * lcols;
-            const float4 x = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * v + cc) * 4));
-            float* d = tile + rr * pitch + cc;
-            d[0] = x.x; d[plane] = x.y; d[2 * plane] = x.z; d[3 * plane] = x.w;
-        }
-    } else {
-        for (int i = tid; i < lrows * lcols; i += THREADS) {
-            const int rr = i / lcols, cc = i - rr * lcols;
-            const float* s = src + ((long long)rr * v + cc) * p.C;
-            float* d = tile + rr * pitch + cc;
-            for (int ch = 0; ch < p.C; ++ch) d[ch * plane] = __ldg(s + ch);
-        }
-    }
-    // ---- every window of the tile starts alive with score 0 (model.py:243-247).  Slot idx = tid + k*THREADS holds
-    // window idx of the tile in row-major order, so a warp's lanes gather adjacent shared-memory words.
-    const int nwin = rows_valid * cols_valid;
-    __syncthreads();
-    unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
-    asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
-    unsigned wa[WPT];
-    float hs[WPT], alive[WPT];         // running score of the slot's window; alive = 1.0f / 0.0f (empty or rejected)
-#pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-        const int idx = tid + k * THREADS;
-        const bool has = idx < nwin;
-        const int lr = has ? idx / cols_valid : 0, lc = has ? idx - lr * cols_valid : 0;
-        wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
-        hs[k] = 0.f;
-        alive[k] = has ? 1.f : 0.f;
-    }
-
-    // slot idx = tid + k*stride.  After a re-pack the survivors are laid out `p.pack` slots per thread over as few
-    // warps as needed, so the per-stage record loads keep being shared by several windows of a thread.
-    // generic path: nodes per stage; depth-4 path: shared-window address of the staged stage records
-    const int aux = MODE == MODE_DK4 ? (int)((unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)p.rec_off) : p.N;
-    int n_slots = nwin, n_alive = nwin, t = 0, round = 0, stride = THREADS;
-    unsigned my_weak = 0;
-    while (t < p.T && n_alive > 0) {
-        // a round = a block of stages every warp runs on its own; rounds get longer as the tile empties
-        int t_end = min(p.T, t + (n_slots > THREADS ? p.round_full : (n_slots > 64 ? p.round_mid : p.round_tail)));
-        if (MODE == MODE_DK4) {
-            // stage this round's stage records in shared memory (all readers of the previous round passed the barrier
-            // that ended it)
-            t_end = min(t_end, t + DK4_ROUND_MAX);
-            const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t);
-            int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
-            for (int i = tid; i < (t_end - t) * (int)(sizeof(StageDK4) / 16); i += THREADS) d[i] = __ldg(g + i);
-            __syncthreads();
-        }
-        bool mine = false;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) mine |= alive[k] != 0.f;
-        if (__any_sync(0xffffffffu, mine)) {
-            // slots of this warp that can hold a window: idx = (warp*32 + lane) + k*stride < n_slots (warp-uniform)
-            const int first = warp << 5;
-            const int kmax = first < stride ? (n_slots - first + stride - 1) / stride : 0;
-            if (WPT >= 8 && kmax > 4) run_round<MODE, WPT >= 8 ? 8 : 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
-            else if (kmax == 4) run_round<MODE, 4, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
-            else if (kmax == 3) run_round<MODE, 3, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
-            else if (kmax == 2) run_round<MODE, 2, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
-            else if (kmax == 1) run_round<MODE, 1, WPT>(tile_base, wa, hs, alive, t, t_end, my_weak, p.nodes, aux, p.theta, p.dk4);
-        }
-        // ---- how many windows of the tile are still alive
-        unsigned bal[WPT];
-        int wcnt = 0;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            bal[k] = __ballot_sync(0xffffffffu, alive[k] != 0.f);
-            wcnt += __popc(bal[k]);
-        }
-        const int par = round % 3;
-        if (lane == 0 && wcnt) atomicAdd(&s_cnt[par], wcnt);
-        if (tid == 0) s_cnt[(round + 1) % 3] = 0;
-        __syncthreads();
-        n_alive = s_cnt[par];
-        t = t_end;
-        ++round;
-        if (n_alive == 0 || t >= p.T) break;
-        if (n_alive * p.compact_den > n_slots * p.compact_num || n_slots <= 32 || n_alive > p.list_cap) continue;
-
-        // ---- order-preserving re-pack of the CTA's survivors into the first n_alive slots
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) s_tot[k * WARPS + warp] = __popc(bal[k]);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            int v_[EPL], sum = 0;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) { v_[e] = s_tot[lane * EPL + e]; sum += v_[e]; }
-            int inc = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            int run = inc - sum;
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) { s_pre[lane * EPL + e] = run; run += v_[e]; }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            if (alive[k] != 0.f) {
-                const int pos = s_pre[k * WARPS + warp] + __popc(bal[k] & ((1u << lane) - 1u));
-                s_woff[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
-                s_score[pos] = hs[k];
-            }
-        }
-        __syncthreads();
-        n_slots = n_alive;
-        // balanced layout: the fewest slots per thread that hold all survivors (pack < 0), or a fixed number, over as
-        // few warps as that takes -- every warp with slots then has the same amount of work in a round
-        {
-            const int per = p.pack < 0 ? (n_slots + THREADS - 1) / THREADS : p.pack;
-            if (per > 0) stride = min(THREADS, ((n_slots + per - 1) / per + 31) & ~31);
-        }
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            const int idx = tid + k * stride;
-            const bool has = tid < stride && idx < n_slots;
-            wa[k] = tile_base + 4u * (has ? (unsigned)s_woff[idx] : 0u);
-            hs[k] = has ? s_score[idx] : 0.f;
-            alive[k] = has ? 1.f : 0.f;
-        }
-    }
-
-    // ---- survivors of all T stages: mask bit + dense score (ranked later by emit_hits)
-#pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-        if (alive[k] != 0.f) {
-            const int wo = (int)((wa[k] - tile_base) >> 2);
-            const int lr = wo / pitch, lc = wo - lr * pitch;
-            const long long widx = win_off + (long long)(r0 + lr) * win_cols + (c0 + lc);
-            p.score[(long long)frame * p.score_stride + widx] = hs[k];
-            atomicOr(p.mask + (long long)frame * p.mask_stride + (widx >> 5), 1u << (unsigned)(widx & 31));
-        }
-    }
-    // ---- stats (model.py:248,252): n_loc += windows, n_weak += windows entering each stage
-    unsigned w = my_weak;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
-    if (lane == 0 && w) atomicAdd(p.stats + 2 * frame + 1, (unsigned long long)w);
-    if (tid == 0) atomicAdd(p.stats + 2 * frame, (unsigned long long)nwin);
-}
-
-// One round of canonical depth-2 stages whose records were staged in shared memory (StageD2S, three broadcast
-// LDS.128 per stage shared by the NK slots of the thread).  Same arithmetic as the constant-bank loop of run_round:
-// left iff X <= threshold (training.py:92), float32 accumulation in stage order (model.py:251), hs >= theta (model.py:255).
-// SPEC: gather both children before the root comparison is known (three independent loads: shortest dependency chain,
-// for warps that are alone on their SM partition); otherwise only the taken child (two loads).
-__device__ __forceinline__ int4 lds_v4(unsigned addr) {
-    int4 v;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-template <int NK, int WPT, bool SPEC>
-__device__ __forceinline__ void run_round_d2s(unsigned recs /* shared-window address of the round's first StageD2S */, int n_stages,
-                                              const unsigned (&wa)[WPT], float (&hs)[WPT], float (&alive)[WPT], unsigned& my_weak) {
-    float entered[NK];
-#pragma unroll
-    for (int k = 0; k < NK; ++k) entered[k] = 0.f;
-#ifndef D2S_UNROLL
-#define D2S_UNROLL 4
-#endif
-    constexpr int kUnroll = D2S_UNROLL;
-#pragma unroll kUnroll
-    for (int s = 0; s < n_stages; ++s) {
-        const unsigned r = recs + (unsigned)s * (unsigned)sizeof(StageD2S);
-        const int4 A = lds_v4(r), BL = lds_v4(r + 16u), BR = lds_v4(r + 32u);
-        const float thr0 = __int_as_float(A.y), theta = __int_as_float(A.z);
-        float x0[NK];
-#pragma unroll
-        for (int k = 0; k < NK; ++k) x0[k] = lds_f32(wa[k] + (unsigned)A.x);
-        if (SPEC) {
-            float xa[NK], xb[NK];
-#pragma unroll
-            for (int k = 0; k < NK; ++k) { xa[k] = lds_f32(wa[k] + (unsigned)BL.x); xb[k] = lds_f32(wa[k] + (unsigned)BR.x); }
-#pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const float pa = (xa[k] <= __int_as_float(BL.y)) ? __int_as_float(BL.z) : __int_as_float(BL.w);
-                const float pb = (xb[k] <= __int_as_float(BR.y)) ? __int_as_float(BR.z) : __int_as_float(BR.w);
-                entered[k] += alive[k];
-                hs[k] += (x0[k] <= thr0) ? pa : pb;
-                alive[k] *= fset_ge(hs[k], theta);
-            }
-        } else {
-            float x1[NK];
-            bool l0[NK];
-#pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                l0[k] = x0[k] <= thr0;
-                x1[k] = lds_f32(wa[k] + (unsigned)(l0[k] ? BL.x : BR.x));
-            }
-#pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const float q0 = __int_as_float(l0[k] ? BL.z : BR.z), q1 = __int_as_float(l0[k] ? BL.w : BR.w);
-                const bool l1 = x1[k] <= __int_as_float(l0[k] ? BL.y : BR.y);
-                entered[k] += alive[k];
-                hs[k] += l1 ? q0 : q1;
-                alive[k] *= fset_ge(hs[k], theta);
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NK; ++k) my_weak += (unsigned)entered[k];
-}
-
-// ---- speculative rounds of the sparse phase (depth-2 models) ---------------------------------------------------------
-// Once a tile is down to a few rows of windows, a round is no longer limited by issue slots but by the latency of one
-// warp walking through the stages in order while most of the CTA idles.  Which leaf a window reaches at a stage does
-// not depend on its score, only the rejection test does, so the round is split in two:
-//   phase A  (all warps) leaf indices, 2 bits per stage, of every window of the round for SPEC_SUB = 32 stages per warp;
-//            warp w works on row w % rp for the stages of sub-block w / rp, so the warps cover up to 8 sub-blocks of the
-//            same windows at once (no dependency between stages);
-//   phase B  (one warp per row) the float32 accumulation in stage order with the theta test and the n_weak count
-//            (model.py:251-255): per stage one lookup in the round's leaf table and a 4-cycle dependency.
-// A window that is rejected early in the round has had its later stages evaluated for nothing; that is the same waste
-// as a dead lane in an ordinary round of the same length.
-constexpr int SPEC_SUB = 32;          // stages per sub-block: 64 bits of leaf indices per window
-constexpr int SPEC_MAX_SUB = 8;       // sub-blocks per round: the leaf table of 256 stages fits the record area
-
-// leaf index bits of one window for the stages [s0, s0 + 32) (clamped to the last stage); the first stage ends up in
-// the highest bits of .x, stage 16 in the highest bits of .y
-__device__ __forceinline__ uint2 d2_leaf_bits(unsigned wa, int s0, int T) {
-    unsigned w[2] = {0u, 0u};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-            const int s = min(s0 + 16 * h + j, T - 1);
-            const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
-            const int4 A = rec[0], B = rec[1];
-            const float x0 = lds_f32(wa + (unsigned)A.x);
-            const bool l0 = x0 <= __int_as_float(B.x);                      // training.py:92 -- left iff X <= threshold
-            const float x1 = lds_f32(wa + (unsigned)(l0 ? A.y : A.z));
-            const bool l1 = x1 <= __int_as_float(l0 ? B.y : B.z);
-            w[h] = (w[h] << 2) + (unsigned)((l0 ? 0 : 2) + (l1 ? 0 : 1));   // leaves in the order LL, LR, RL, RR
-        }
-    }
-    return make_uint2(w[0], w[1]);
-}
-
-// float32 accumulation of nst <= 32 stages in stage order from their leaf bits; lt / th: shared-window byte addresses of
-// the leaf table entry {LL, LR, RL, RR} and of theta of the first of these stages
-__device__ __forceinline__ void d2_accumulate(unsigned lt, unsigned th, uint2 bits, int nst, float& hs, float& alive, float& entered) {
-#pragma unroll 4
-    for (int j = 0; j < nst; ++j) {
-        const unsigned w = j < 16 ? bits.x : bits.y;
-        const unsigned idx4 = __funnelshift_l(w, w, 2 * (j & 15) + 4) & 0xcu;   // field j rotated to bits [3:2]
-        float leaf, theta;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(leaf) : "r"(lt + 16u * (unsigned)j + idx4));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(theta) : "r"(th + 4u * (unsigned)j));
-        entered += alive;                                   // model.py:252
-        hs += leaf;                                         // model.py:251 -- float32, stage order
-        alive *= fset_ge(hs, theta);                        // model.py:255
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ pool kernel
 // Same tile, patch and stage loops as cascade_kernel, different bookkeeping between rounds: after EVERY round the
 // survivors of the CTA are appended to a pool in shared memory (window offset + running score; one shared-memory
@@ -629,6 +335,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
         int nk = (rows + WARPS - 1) / WARPS;
         nk = min(min(max(nk, p.pack), rows), WPT);
         const int row0 = warp * nk;
+        // (a warp without rows skips the slot bookkeeping of the round; it only takes part in the barriers)
+        if (row0 < rows || !pooled)
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const int idx = (row0 + k) * 32 + lane;
@@ -644,68 +352,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
                 hs[k] = has ? pool_hs[idx] : 0.f;
             }
             alive[k] = has ? 1.f : 0.f;
-        }
-        if (MODE == MODE_D2 && pooled && n <= p.spec_n) {
-            // ---- speculative round: rp rows x G sub-blocks of 32 stages, one (row, sub-block) per warp
-            const int rp = rows <= 1 ? 1 : (rows <= 2 ? 2 : (rows <= 4 ? 4 : 8));
-            const int G = min(min(WARPS / rp, SPEC_MAX_SUB), (p.T - t + SPEC_SUB - 1) / SPEC_SUB);
-            const int R = min(G * SPEC_SUB, p.T - t);
-            const int row = warp % rp, sub = warp / rp;
-            float4* s_lt = reinterpret_cast<float4*>(smem_raw + p.rec_off);                 // [R] leaves LL, LR, RL, RR
-            float* s_th = reinterpret_cast<float*>(smem_raw + p.rec_off) + 4 * SPEC_SUB * SPEC_MAX_SUB;   // [R] theta
-            uint2* s_bits = reinterpret_cast<uint2*>(pool_hs + p.list_cap / 2);             // [warp][lane], above the live pool entries
-            // the round's leaf table (every reader of the previous one passed the barrier that ended its round)
-            for (int i = tid; i < R; i += THREADS) {
-                const StageD2S* __restrict__ r = p.d2s + t + i;
-                s_lt[i] = make_float4(r->pLL, r->pLR, r->pRL, r->pRR);
-                s_th[i] = r->theta;
-            }
-            const int idx = row * 32 + lane;
-            const bool has = row < rows && idx < n;
-            const unsigned my_wa = tile_base + 4u * (has ? (unsigned)pool_wo[idx] : 0u);
-            float my_hs = has ? pool_hs[idx] : 0.f, my_alive = (has && sub == 0) ? 1.f : 0.f;
-            if (row < rows && sub < G) s_bits[warp * 32 + lane] = d2_leaf_bits(my_wa, t + sub * SPEC_SUB, p.T);
-            __syncthreads();
-            if (p.dbg && tid == 0) { atomicAdd(p.dbg + 0, (unsigned long long)(32 * rows) * (unsigned)R); atomicAdd(p.dbg + 5, 1ull); }
-            if (warp < rows) {
-                // phase B: this warp's row (it is the sub-block 0 warp of the row, so wa / hs are already in registers)
-                const unsigned lt0 = (unsigned)__cvta_generic_to_shared(s_lt), th0 = (unsigned)__cvta_generic_to_shared(s_th);
-                float entered = 0.f;
-                for (int g = 0; g < G; ++g) {
-                    const uint2 bits = s_bits[(g * rp + row) * 32 + lane];
-                    d2_accumulate(lt0 + 16u * (unsigned)(g * SPEC_SUB), th0 + 4u * (unsigned)(g * SPEC_SUB), bits,
-                                  min(SPEC_SUB, R - g * SPEC_SUB), my_hs, my_alive, entered);
-                    if (!__any_sync(0xffffffffu, my_alive != 0.f)) break;
-                }
-                my_weak += (unsigned)entered;
-            }
-            t += R;
-            const bool live = warp < rows && my_alive != 0.f;
-            if (t >= p.T) {
-                // the cascade is complete: keep the survivor in slot 0 for the epilogue
-                wa[0] = my_wa; hs[0] = my_hs; alive[0] = live ? 1.f : 0.f;
-#pragma unroll
-                for (int k = 1; k < WPT; ++k) alive[k] = 0.f;
-                break;
-            }
-            const unsigned bal0 = __ballot_sync(0xffffffffu, live);
-            int base0 = 0;
-            if (lane == 0 && bal0) base0 = atomicAdd(&s_tail[par], __popc(bal0));
-            base0 = __shfl_sync(0xffffffffu, base0, 0);
-            if (live) {                                   // (every pool entry of the round was read before the barrier above)
-                const int pos = base0 + __popc(bal0 & ((1u << lane) - 1u));
-                pool_wo[pos] = (unsigned short)((my_wa - tile_base) >> 2);
-                pool_hs[pos] = my_hs;
-            }
-            if (tid == 0) s_t = t;
-            __syncthreads();
-            n = s_tail[par];
-            t = s_t;
-            if (tid == 0) s_tail[par ^ 1] = 0;
-            par ^= 1;
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) alive[k] = 0.f;
-            continue;
         }
         if (solo) {
             // at most 32 windows are left: warp 0 finishes the cascade on its own, nobody meets at a barrier any more
@@ -747,26 +393,28 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
         t = t_end;
         if (t >= p.T) break;
         // ---- append the survivors to the pool (unordered across warps, one atomic per warp)
-        unsigned bal[WPT];
-        int wcnt = 0;
+        if (row0 < rows) {
+            unsigned bal[WPT];
+            int wcnt = 0;
 #pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            bal[k] = __ballot_sync(0xffffffffu, alive[k] != 0.f);
-            wcnt += __popc(bal[k]);
-        }
-        int base = 0;
-        if (lane == 0 && wcnt) base = atomicAdd(&s_tail[par], wcnt);
-        base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            if (alive[k] != 0.f) {
-                const int pos = base + __popc(bal[k] & ((1u << lane) - 1u));
-                pool_wo[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
-                pool_hs[pos] = hs[k];
+            for (int k = 0; k < WPT; ++k) {
+                bal[k] = __ballot_sync(0xffffffffu, alive[k] != 0.f);
+                wcnt += __popc(bal[k]);
             }
-            base += __popc(bal[k]);
+            int base = 0;
+            if (lane == 0 && wcnt) base = atomicAdd(&s_tail[par], wcnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int k = 0; k < WPT; ++k) {
+                if (alive[k] != 0.f) {
+                    const int pos = base + __popc(bal[k] & ((1u << lane) - 1u));
+                    pool_wo[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
+                    pool_hs[pos] = hs[k];
+                }
+                base += __popc(bal[k]);
+            }
+            if (p.dbg && lane == 0) atomicAdd(p.dbg + 6, (unsigned long long)wcnt);
         }
-        if (p.dbg && lane == 0) atomicAdd(p.dbg + 6, (unsigned long long)wcnt);
         if (tid == 0) s_t = t;
         __syncthreads();
         n = s_tail[par];
@@ -806,414 +454,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
         if (lane == 0 && w) atomicAdd(p.dbg + 4, (unsigned long long)w);
         if (tid == 0) atomicAdd(p.dbg + 7, 1ull);
     }
-}
-
-// ------------------------------------------------------------------------------------------------ class kernel
-// The pool kernel's rounds, with the pool organised so that the gathers of a warp stay free of shared-memory bank
-// conflicts after rejection has thinned the tile.  The bank a window touches at stage s is (window offset + feature
-// offset) mod 32, so a row of 32 windows is conflict-free at EVERY stage iff their window offsets are distinct mod 32.
-// Windows are therefore kept in 32 "class" lists (class = window offset mod 32, 64 windows each for a 32 x 64 tile) and
-// lane l of every warp works on class l:
-//   * a survivor normally stays in its lane.  Its list position is a prefix sum over the (warp, slot) order of the
-//     per-thread survivor counts -- one byte per (lane, warp) in shared memory, read back as one 16-byte word -- so
-//     no atomics and no cross-lane traffic are needed for these "host" windows;
-//   * lists differ in length after random rejection.  With n survivors the pool keeps cut = ceil(n / 32) rows; the
-//     windows of a list beyond `cut` become "guests": they fill the holes that shorter lists leave in those rows (a
-//     guest shares its bank with the host of its class in the same row -- a 2-way conflict in that row only).  Guest
-//     survivors are counted with one shared-memory atomic per window (they are the minority);
-//   * holes and excess are enumerated with one packed warp scan that every warp does redundantly, so the loader of
-//     the next round needs two barriers per round and no tables.
-// Falls back to cascade_pool_kernel when the tile is not a multiple of 32 windows wide.
-// One round of stages [t, te) over the first nk window slots of a thread (nk is warp-uniform).  Depth-2 models read the
-// stage records either from the round's shared-memory copy (nk <= sm_maxnk) or from the constant bank.
-#ifndef CLASS_SM_MAXNK
-#define CLASS_SM_MAXNK 2     // depth-2 rounds with at most this many window slots per thread read the staged records
-#endif
-// The stage loops of the class kernel are separate (non-inlined) functions that take and return the window slots by
-// value: the loops then get the whole register budget of the kernel to themselves, and what the round bookkeeping keeps
-// alive across a round is saved once around the call instead of being spilled and re-loaded inside the loops.
-struct Slots {
-    unsigned wa[4];
-    float hs[4], alive[4];
-    unsigned weak;
-};
-template <int NK, bool SPEC>
-__device__ __noinline__ Slots round_d2_shared(Slots s, unsigned recs, int n_stages) {
-    run_round_d2s<NK, 4, SPEC>(recs, n_stages, s.wa, s.hs, s.alive, s.weak);
-    return s;
-}
-template <int MODE, int NK>
-__device__ __noinline__ Slots round_generic(Slots s, unsigned tile_base, int t, int te, const NodeDev* nodes, int aux,
-                                            const float* theta, const StageDK4* dk4) {
-    run_round<MODE, NK, 4>(tile_base, s.wa, s.hs, s.alive, t, te, s.weak, nodes, aux, theta, dk4);
-    return s;
-}
-template <int MODE>
-__device__ __forceinline__ Slots run_stages(const CascadeParams& p, unsigned char* smem_raw, unsigned tile_base, int nk, const Slots& s,
-                                            int t, int te) {
-    // shared-window address of the staged stage records (depth-2 / depth-4 paths); generic path: nodes per stage
-    const unsigned rec_addr = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)p.rec_off;
-    if (MODE == MODE_D2) {
-        // few slots per thread: stage records from the round's shared-memory copy (fixed ~30-cycle latency); many slots:
-        // records from the constant bank through the uniform datapath (no address adds, latency hidden by the other warps)
-        if (nk == 1) return CLASS_SM_MAXNK >= 1 ? round_d2_shared<1, true>(s, rec_addr, te - t) : round_generic<MODE_D2, 1>(s, tile_base, t, te, p.nodes, p.N, p.theta, p.dk4);
-        if (nk == 2) return CLASS_SM_MAXNK >= 2 ? round_d2_shared<2, false>(s, rec_addr, te - t) : round_generic<MODE_D2, 2>(s, tile_base, t, te, p.nodes, p.N, p.theta, p.dk4);
-        if (nk == 3) return CLASS_SM_MAXNK >= 3 ? round_d2_shared<3, false>(s, rec_addr, te - t) : round_generic<MODE_D2, 3>(s, tile_base, t, te, p.nodes, p.N, p.theta, p.dk4);
-        return CLASS_SM_MAXNK >= 4 ? round_d2_shared<4, false>(s, rec_addr, te - t) : round_generic<MODE_D2, 4>(s, tile_base, t, te, p.nodes, p.N, p.theta, p.dk4);
-    }
-    const int aux = MODE == MODE_DK4 ? (int)rec_addr : p.N;
-    if (nk == 4) return round_generic<MODE, 4>(s, tile_base, t, te, p.nodes, aux, p.theta, p.dk4);
-    if (nk == 3) return round_generic<MODE, 3>(s, tile_base, t, te, p.nodes, aux, p.theta, p.dk4);
-    if (nk == 2) return round_generic<MODE, 2>(s, tile_base, t, te, p.nodes, aux, p.theta, p.dk4);
-    return round_generic<MODE, 1>(s, tile_base, t, te, p.nodes, aux, p.theta, p.dk4);
-}
-
-// Stage records of stages [t0, t1) -> shared memory (read by the rounds that follow the next barrier).
-template <int MODE>
-__device__ __forceinline__ void stage_records(const CascadeParams& p, unsigned char* smem_raw, int t0, int t1, int first, int step) {
-    if (MODE == MODE_DK4) {
-        const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t0);
-        int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
-        for (int i = first; i < (t1 - t0) * (int)(sizeof(StageDK4) / 16); i += step) d[i] = __ldg(g + i);
-    } else if (MODE == MODE_D2) {
-        const int4* __restrict__ g = reinterpret_cast<const int4*>(p.d2s + t0);
-        int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
-        for (int i = first; i < (t1 - t0) * (int)(sizeof(StageD2S) / 16); i += step) d[i] = __ldg(g + i);
-    }
-}
-// Stages per round while n_left windows of the tile are alive (capped by what the staged records hold).
-template <int MODE>
-__device__ __forceinline__ int cas_round_len(const CascadeParams& p, int n_left) {
-    constexpr int ROUND_MAX = MODE == MODE_DK4 ? DK4_ROUND_MAX : (MODE == MODE_D2 ? D2S_ROUND_MAX : (1 << 30));
-    return min(ROUND_MAX, n_left > p.round_n1 ? p.round_full : (n_left > p.round_n2 ? p.round_mid : p.round_tail));
-}
-
-__device__ __forceinline__ unsigned bytesum4(unsigned x, unsigned acc) { return __dp4a(x, 0x01010101u, acc); }
-
-// Round state of the class kernel, at the start of its dynamic shared memory (the patch, the pool and the staged stage
-// records follow at CLS_CTL_BYTES).  It also holds a copy of the kernel parameters: the pieces below are non-inlined
-// functions, and a kernel parameter whose address is passed to a function would be copied to local memory first.  Everything the pieces of the kernel hand
-// to one another between rounds lives here or in the slots, so that each piece (separate, non-inlined functions) can
-// use the kernel's whole register budget on its own.
-struct ClassCtl {
-    CascadeParams p;         // copy of the kernel parameters
-    unsigned cnt8[128];      // [lane][warp] bytes: host survivors of that thread in the round that just ended
-    int ov[2][32];           // guest survivors per class (double-buffered by round parity)
-    int len[32], hb[32];     // per class: list length, index of its first hole (pool geometry of the next round)
-    int n, te, rows;         // next round: windows, end stage, rows of 32 windows
-    int cut, n_ovf, h_tot;   // pool geometry: rows of class lists, excess windows, holes
-    int par, first;          // parity of `ov`, 1 before the first re-pack
-    long long dbg_t0;        // time stamp of the running phase (debug counters)
-    int dbg_cat, pad_;
-};
-extern __shared__ __align__(16) unsigned char cas_smem[];
-constexpr int CLS_CTL_BYTES = (int)((sizeof(ClassCtl) + 127) / 128 * 128);
-__device__ __forceinline__ ClassCtl* cls_ctl() { return reinterpret_cast<ClassCtl*>(cas_smem); }
-__device__ __forceinline__ unsigned char* cls_dyn() { return cas_smem + CLS_CTL_BYTES; }
-
-struct TileGeom {
-    int frame, r0, c0, rows_valid, cols_valid, win_cols, v;
-    long long chn_off, win_off;
-};
-__device__ __forceinline__ TileGeom tile_geom(const CascadeParams& p) {
-    TileGeom g;
-    g.frame = blockIdx.x / p.tiles_per_frame;
-    const int tile_id = blockIdx.x - g.frame * p.tiles_per_frame;
-    const LevelDev* __restrict__ L = p.levels + find_level_by_ctile(p.levels, p.n_levels, tile_id);
-    const int local = tile_id - L->ctile0;
-    const int ty = local / L->ctiles_x, tx = local - ty * L->ctiles_x;
-    g.r0 = ty * p.TR; g.c0 = tx * p.TC;
-    g.rows_valid = min(p.TR, L->win_rows - g.r0); g.cols_valid = min(p.TC, L->win_cols - g.c0);
-    g.win_cols = L->win_cols; g.v = L->v; g.chn_off = L->chn_off; g.win_off = L->win_off;
-    return g;
-}
-__device__ __forceinline__ void cls_dbg_phase(const CascadeParams& p, ClassCtl* ctl, int next_cat) {
-    if (p.dbg && threadIdx.x == 0) {
-        const long long c = clock64();
-        atomicAdd(p.dbg + ctl->dbg_cat, (unsigned long long)(c - ctl->dbg_t0));
-        ctl->dbg_t0 = c;
-        ctl->dbg_cat = next_cat;
-    }
-}
-
-// Prologue: the tile's channel patch (HWC in HBM -> planar in shared memory), the stage records of the first round,
-// the round state.  Returns the number of windows of the tile.
-template <int MODE, int THREADS>
-__device__ __noinline__ int cls_prologue() {
-    const int tid = threadIdx.x;
-    ClassCtl* ctl = cls_ctl();
-    const CascadeParams& p = ctl->p;
-    float* tile = reinterpret_cast<float*>(cls_dyn());
-    const TileGeom g = tile_geom(p);
-    const int lrows = g.rows_valid + p.m - 1, lcols = g.cols_valid + p.n - 1;
-    const int pitch = p.pitch, plane = p.plane;
-    const int nwin = g.rows_valid * g.cols_valid;
-    if (tid < 64) ctl->ov[tid >> 5][tid & 31] = 0;
-    const int te = min(p.T, cas_round_len<MODE>(p, nwin));
-    if (tid == 0) {
-        ctl->n = nwin; ctl->te = te; ctl->rows = g.rows_valid * ((g.cols_valid + 31) >> 5);
-        ctl->cut = 0; ctl->n_ovf = 0; ctl->h_tot = 0; ctl->par = 0; ctl->first = 1;
-        ctl->dbg_t0 = p.dbg ? clock64() : 0; ctl->dbg_cat = 9;
-    }
-    stage_records<MODE>(p, cls_dyn(), 0, te, tid, THREADS);
-    const float* __restrict__ src = p.chns + (long long)g.frame * p.chn_stride + g.chn_off + ((long long)g.r0 * g.v + g.c0) * p.C;
-    if (p.C == 4) {
-        for (int i = tid; i < lrows * lcols; i += THREADS) {
-            const int rr = i / lcols, cc = i - rr * lcols;
-            const float4 x = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * g.v + cc) * 4));
-            float* d = tile + rr * pitch + cc;
-            d[0] = x.x; d[plane] = x.y; d[2 * plane] = x.z; d[3 * plane] = x.w;
-        }
-    } else {
-        for (int i = tid; i < lrows * lcols; i += THREADS) {
-            const int rr = i / lcols, cc = i - rr * lcols;
-            const float* s = src + ((long long)rr * g.v + cc) * p.C;
-            float* d = tile + rr * pitch + cc;
-            for (int ch = 0; ch < p.C; ++ch) d[ch * plane] = __ldg(s + ch);
-        }
-    }
-    __syncthreads();
-    cls_dbg_phase(p, ctl, 10);
-    return nwin;
-}
-
-// Loader: this thread's window slots for the round described by the round state.  Row j of the round goes to
-// (warp j / nk, slot j % nk).  First round: row j = (tile row j / halves, column half j % halves) and lane l takes the
-// window of class l; later rounds: the lane's own class list, a guest in a hole, or a row of excess windows.
-template <int THREADS>
-__device__ __noinline__ Slots cls_load(int nk, unsigned weak) {
-    constexpr int WPT = 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const ClassCtl* ctl = cls_ctl();
-    const CascadeParams& p = ctl->p;
-    const float* pool_hs = reinterpret_cast<const float*>(cls_dyn()) + ((p.C * p.plane + 3) & ~3);
-    const unsigned short* pool_wo = reinterpret_cast<const unsigned short*>(pool_hs + p.list_cap);
-    const unsigned tile_base = (unsigned)__cvta_generic_to_shared(cls_dyn());
-    const int rows = ctl->rows, row0 = warp * nk;
-    Slots S;
-    S.weak = weak;
-    int n_guest = 0;
-    if (ctl->first) {
-        const int tile_id = blockIdx.x % p.tiles_per_frame;
-        const LevelDev* __restrict__ L = p.levels + find_level_by_ctile(p.levels, p.n_levels, tile_id);
-        const int tx = (tile_id - L->ctile0) % L->ctiles_x;
-        const int cols_valid = min(p.TC, L->win_cols - tx * p.TC);
-        const int halves = (cols_valid + 31) >> 5;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            const int j = row0 + k;
-            const bool in_row = k < nk && j < rows;
-            const int lr = in_row ? j / halves : 0, hf = j - lr * halves;
-            const int lc = ((lane - lr * p.pitch) & 31) + 32 * hf;
-            const bool has = in_row && lc < cols_valid;
-            // an empty lane still executes the gathers: park it on a word of its own bank (class = lane)
-            S.wa[k] = tile_base + 4u * (unsigned)(has ? lr * p.pitch + lc : lane);
-            S.hs[k] = 0.f;
-            S.alive[k] = has ? 1.f : 0.f;
-        }
-    } else {
-        const int len_l = ctl->len[lane], hb_l = ctl->hb[lane], cut = ctl->cut, n_ovf = ctl->n_ovf, h_tot = ctl->h_tot;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            const int j = row0 + k;
-            int idx = -1;
-            if (k < nk && j < rows) {
-                if (j < cut) {
-                    if (j < len_l) idx = j * 32 + lane;                       // the lane's own class
-                    else { const int g = hb_l + (j - len_l); if (g < n_ovf) { idx = cut * 32 + g; ++n_guest; } }
-                } else {
-                    const int g = h_tot + (j - cut) * 32 + lane;                 // rows made of excess windows only
-                    if (g < n_ovf) { idx = cut * 32 + g; ++n_guest; }
-                }
-            }
-            const bool has = idx >= 0;
-            S.wa[k] = tile_base + 4u * (has ? (unsigned)pool_wo[idx] : (unsigned)lane);
-            S.hs[k] = has ? pool_hs[idx] : 0.f;
-            S.alive[k] = has ? 1.f : 0.f;
-        }
-    }
-    if (p.dbg && n_guest) atomicAdd(p.dbg + 8, (unsigned long long)n_guest);
-    return S;
-}
-
-// Re-pack after a round that ended at stage t: count the survivors (hosts per (lane, warp) as bytes, guests per class
-// with an atomic), derive the pool geometry of the next round, stage the next round's stage records and move the
-// survivors to their list positions.  Returns the number of survivors of the tile (0: the tile is finished).
-template <int MODE, int THREADS>
-__device__ __noinline__ int cls_repack(Slots S, bool busy, int t) {
-    constexpr int WARPS = THREADS / 32, WPT = 4, CW = WARPS / 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    ClassCtl* ctl = cls_ctl();
-    const CascadeParams& p = ctl->p;
-    float* pool_hs = reinterpret_cast<float*>(cls_dyn()) + ((p.C * p.plane + 3) & ~3);
-    unsigned short* pool_wo = reinterpret_cast<unsigned short*>(pool_hs + p.list_cap);
-    const unsigned tile_base = (unsigned)__cvta_generic_to_shared(cls_dyn());
-    const int par = ctl->par;
-    int cls[WPT], grank[WPT], c_host = 0;
-#pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-        cls[k] = (int)(((S.wa[k] - tile_base) >> 2) & 31u);
-        grank[k] = -1;                                              // -1: host (or dead)
-        if (busy && S.alive[k] != 0.f) {
-            if (cls[k] == lane) ++c_host;
-            else grank[k] = atomicAdd(&ctl->ov[par][cls[k]], 1);
-        }
-    }
-    reinterpret_cast<unsigned char*>(ctl->cnt8)[lane * WARPS + warp] = (unsigned char)c_host;
-    __syncthreads();
-    unsigned host_tot = 0, prefix = 0;
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-        const unsigned q = ctl->cnt8[lane * CW + i];
-        // bytes of the (lane, warp) counters that belong to warps before this one
-        const unsigned pm = warp >= 4 * i + 4 ? 0xffffffffu : (warp <= 4 * i ? 0u : (1u << (8 * (warp - 4 * i))) - 1u);
-        host_tot = bytesum4(q, host_tot);
-        prefix = bytesum4(q & pm, prefix);
-    }
-    const int len_l = (int)host_tot + ctl->ov[par][lane];
-    const int n = __reduce_add_sync(0xffffffffu, len_l);
-    if (tid < 32) ctl->ov[par ^ 1][tid] = 0;
-    if (n == 0) return 0;
-    // the next round's stage records (every reader of the old ones has passed the barrier above)
-    const int te = min(p.T, t + cas_round_len<MODE>(p, n));
-    stage_records<MODE>(p, cls_dyn(), t, te, tid, THREADS);
-    // ---- pool geometry: cut rows of class lists; excess windows (list position >= cut) fill the holes
-    int cut = (n + 31) >> 5;
-    int e_l, eb_l, hb_l, n_ovf, h_tot;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        e_l = max(len_l - cut, 0);
-        const int h_l = max(cut - len_l, 0);
-        unsigned inc = ((unsigned)e_l << 16) | (unsigned)h_l;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        const unsigned totals = __shfl_sync(0xffffffffu, inc, 31);
-        eb_l = (int)(inc >> 16) - e_l;
-        hb_l = (int)(inc & 0xffffu) - h_l;
-        n_ovf = (int)(totals >> 16);
-        h_tot = (int)(totals & 0xffffu);
-        if (cut * 32 + n_ovf <= p.list_cap) break;
-        cut = 0;                                                    // (cannot happen for balanced classes) plain pool
-    }
-    // ---- move the survivors to their list positions
-    if (busy) {
-        int run_pos = (int)prefix;
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            const int b = cls[k];
-            const int host_b = __shfl_sync(0xffffffffu, (int)host_tot, b);
-            const int eb_b = __shfl_sync(0xffffffffu, eb_l, b);
-            if (S.alive[k] != 0.f) {
-                int pos, ebase, col;
-                if (grank[k] < 0) { pos = run_pos++; ebase = eb_l; col = lane; }
-                else { pos = host_b + grank[k]; ebase = eb_b; col = b; }
-                const int idx = pos < cut ? pos * 32 + col : cut * 32 + ebase + (pos - cut);
-                pool_wo[idx] = (unsigned short)((S.wa[k] - tile_base) >> 2);
-                pool_hs[idx] = S.hs[k];
-            }
-        }
-    }
-    if (warp == 0) { ctl->len[lane] = len_l; ctl->hb[lane] = hb_l; }
-    if (tid == 0) {
-        ctl->n = n; ctl->te = te; ctl->rows = cut + ((max(n_ovf - h_tot, 0) + 31) >> 5);
-        ctl->cut = cut; ctl->n_ovf = n_ovf; ctl->h_tot = h_tot; ctl->par = par ^ 1; ctl->first = 0;
-        if (p.dbg) atomicAdd(p.dbg + 6, (unsigned long long)n);
-    }
-    cls_dbg_phase(p, ctl, n > 1024 ? 11 : (n > 512 ? 12 : (n > 128 ? 13 : (n > 32 ? 14 : 15))));
-    __syncthreads();
-    return n;
-}
-
-// Epilogue: survivors of all T stages set their bit in the window mask and store their score (ranked later by
-// emit_hits); stats (model.py:248,252): n_loc += windows, n_weak += windows entering each stage.
-template <int THREADS>
-__device__ __noinline__ void cls_epilogue(Slots S) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const ClassCtl* ctl = cls_ctl();
-    const CascadeParams& p = ctl->p;
-    const TileGeom g = tile_geom(p);
-    const int nwin = g.rows_valid * g.cols_valid;
-    const unsigned tile_base = (unsigned)__cvta_generic_to_shared(cls_dyn());
-    if (p.T == 0) {
-        // a cascade without stages keeps every window with score 0 (model.py:247-259 never enters the loop)
-        for (int idx = tid; idx < nwin; idx += THREADS) {
-            const int lr = idx / g.cols_valid, lc = idx - lr * g.cols_valid;
-            mark_survivor(p, g.frame, g.win_off + (long long)(g.r0 + lr) * g.win_cols + (g.c0 + lc), 0.f);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (S.alive[k] != 0.f) {
-                const int wo = (int)((S.wa[k] - tile_base) >> 2);
-                const int lr = wo / p.pitch, lc = wo - lr * p.pitch;
-                mark_survivor(p, g.frame, g.win_off + (long long)(g.r0 + lr) * g.win_cols + (g.c0 + lc), S.hs[k]);
-            }
-        }
-    }
-    unsigned w = S.weak;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
-    if (lane == 0 && w) atomicAdd(p.stats + 2 * g.frame + 1, (unsigned long long)w);
-    if (tid == 0) atomicAdd(p.stats + 2 * g.frame, (unsigned long long)nwin);
-    if (p.dbg) {
-        if (lane == 0 && w) atomicAdd(p.dbg + 4, (unsigned long long)w);
-        if (tid == 0) {
-            atomicAdd(p.dbg + ctl->dbg_cat, (unsigned long long)(clock64() - ctl->dbg_t0));
-            atomicAdd(p.dbg + 7, 1ull);
-        }
-    }
-}
-
-template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) cascade_class_kernel(const CascadeParams p) {
-    constexpr int WARPS = THREADS / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ClassCtl* ctl = cls_ctl();
-    if (threadIdx.x == 0) ctl->p = p;
-    __syncthreads();
-    int n = cls_prologue<MODE, THREADS>();
-    const unsigned tile_base = (unsigned)__cvta_generic_to_shared(cls_dyn());
-    Slots S;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { S.wa[k] = tile_base; S.hs[k] = 0.f; S.alive[k] = 0.f; }
-    S.weak = 0;
-    int t = 0;
-    while (n > 0 && t < p.T) {
-        const int rows = ctl->rows;
-        int te = ctl->te;
-        int nk = (rows + WARPS - 1) / WARPS;
-        nk = min(min(max(nk, p.pack), rows), 4);
-        const bool busy = warp * nk < rows;         // warp-uniform: this warp has rows in this round
-        if (busy) S = cls_load<THREADS>(nk, S.weak);
-        if (rows == 1) {
-            // at most 32 windows are left: warp 0 finishes the cascade on its own, nobody meets at a barrier any more
-            if (warp != 0) break;
-            while (true) {
-                S = run_stages<MODE>(p, cls_dyn(), tile_base, 1, S, t, te);
-                if (p.dbg && lane == 0) { atomicAdd(p.dbg + 0, 32ull * (unsigned)(te - t)); atomicAdd(p.dbg + 5, 1ull); }
-                t = te;
-                if (t >= p.T || !__any_sync(0xffffffffu, S.alive[0] != 0.f)) break;
-                te = min(p.T, t + cas_round_len<MODE>(p, 1));
-                __syncwarp();
-                stage_records<MODE>(p, cls_dyn(), t, te, lane, 32);
-                __syncwarp();
-            }
-            break;
-        }
-        if (busy) {
-            S = run_stages<MODE>(p, cls_dyn(), tile_base, nk, S, t, te);
-            if (p.dbg && lane == 0) atomicAdd(p.dbg + (nk - 1), (unsigned long long)(32 * min(nk, rows - warp * nk) * (te - t)));
-        }
-        if (p.dbg && threadIdx.x == 0) atomicAdd(p.dbg + 5, 1ull);
-        t = te;
-        if (t >= p.T) break;
-        n = cls_repack<MODE, THREADS>(S, busy, t);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) S.alive[k] = 0.f;       // what this thread held now lives in the pool
-    }
-    cls_epilogue<THREADS>(S);
 }
 
 // ------------------------------------------------------------------------------------------------ ranking
@@ -1439,7 +679,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
 
     CascadeParams p;
     p.chns = chns; p.chn_stride = chn_stride; p.levels = d_levels; p.n_levels = n_levels; p.tiles_per_frame = tiles_per_frame;
-    p.nodes = model->d_nodes; p.dk4 = model->d_dk4; p.d2s = model->d_d2s; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
+    p.nodes = model->d_nodes; p.dk4 = model->d_dk4; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
     p.C = model->C; p.m = model->m; p.n = model->n;
     p.TR = model->geom.TR; p.TC = model->geom.TC; p.pitch = model->geom.pitch; p.plane = model->geom.plane;
     p.mask = w.mask; p.mask_stride = windows / 32; p.score = w.score; p.score_stride = windows; p.stats = stats;
@@ -1449,14 +689,10 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const CascadeGeom& g = model->geom;
     p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
-    p.pack = -1;                                 // (v2 kernel: automatic balanced layout after a re-pack)
     const bool use_dk4 = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
     p.rec_off = (g.smem_bytes + 15) & ~15;
-    p.sm_maxnk = g.sm_maxnk;
-    p.spec_n = model->all_d2 ? g.spec_n : 0;
-    // dynamic shared memory: [round state of the class kernel] patch | pool | staged stage records
-    const int smem = (use_dk4 ? p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4)
-                              : (model->all_d2 ? p.rec_off + D2S_ROUND_MAX * (int)sizeof(StageD2S) : p.rec_off)) + CLS_CTL_BYTES;
+    // dynamic shared memory: patch | survivor pool | stage records of a round (depth-4 path)
+    const int smem = use_dk4 ? p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4) : g.smem_bytes;
     // The depth-2 stage table lives in the constant bank, which is one per device.  Loading it is ordered with
     // events, never with a host-side wait: the copy is enqueued on the launching stream after that stream has been
     // made to wait for the last cascade launched on every other stream (they may still read the old table), and
@@ -1481,14 +717,8 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     }
     p.round_n1 = g.round_n1; p.round_n2 = g.round_n2;
     p.dbg = g_dbg_on.load() ? wbg_debug_counters_device() : nullptr;
-    const char* kern = getenv("WBG_CAS_KERNEL");
-    const bool pool_kernel = !(kern && !strcmp(kern, "v2"));
-    // the class kernel needs tile rows that are whole groups of 32 windows
-    const bool class_kernel = pool_kernel && (g.TC % 32) == 0 && !(kern && !strcmp(kern, "pool"));
-    if (pool_kernel) {
-        p.pack = g.pack < 1 ? 1 : (g.pack > 4 ? 4 : g.pack);
-        p.round_tail = g.round_tail;
-    }
+    p.pack = g.pack < 1 ? 1 : (g.pack > 4 ? 4 : g.pack);
+    p.round_tail = g.round_tail;
 #define WBG_CAS_LAUNCH_K(KERNEL, TH)                                                                          \
     do {                                                                                                      \
         WBG_CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
@@ -1506,34 +736,10 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
         else if (use_dk4) WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_DK4, TH>), TH);                          \
         else WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_GENERIC, TH>), TH);                                   \
     } while (0)
-#define WBG_CAS_LAUNCH_CLASS(TH)                                                                              \
-    do {                                                                                                      \
-        if (model->all_d2) WBG_CAS_LAUNCH_K((cascade_class_kernel<MODE_D2, TH>), TH);                         \
-        else if (use_dk4) WBG_CAS_LAUNCH_K((cascade_class_kernel<MODE_DK4, TH>), TH);                         \
-        else WBG_CAS_LAUNCH_K((cascade_class_kernel<MODE_GENERIC, TH>), TH);                                  \
-    } while (0)
-#define WBG_CAS_LAUNCH_MODE(TH, WP)                                                                           \
-    do {                                                                                                      \
-        if (model->all_d2) WBG_CAS_LAUNCH_K((cascade_kernel<MODE_D2, TH, WP>), TH);                           \
-        else if (use_dk4) WBG_CAS_LAUNCH_K((cascade_kernel<MODE_DK4, TH, WP>), TH);                           \
-        else WBG_CAS_LAUNCH_K((cascade_kernel<MODE_GENERIC, TH, WP>), TH);                                    \
-    } while (0)
-    if (pool_kernel) {
-        WBG_REQUIRE(g.wpt == 4 && (g.threads == 512 || g.threads == 256), "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
-        if (class_kernel) {
-            if (g.threads == 512) WBG_CAS_LAUNCH_CLASS(512);
-            else WBG_CAS_LAUNCH_CLASS(256);
-        } else if (g.threads == 512) WBG_CAS_LAUNCH_POOL(512);
-        else WBG_CAS_LAUNCH_POOL(256);
-    } else if (g.threads == 512 && g.wpt == 4) {
-        WBG_CAS_LAUNCH_MODE(512, 4);
-    } else {
-        WBG_REQUIRE(g.threads == 256 && g.wpt == 4, "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
-        WBG_CAS_LAUNCH_MODE(256, 4);
-    }
-#undef WBG_CAS_LAUNCH_MODE
+    WBG_REQUIRE(g.wpt == 4 && (g.threads == 512 || g.threads == 256), "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
+    if (g.threads == 512) WBG_CAS_LAUNCH_POOL(512);
+    else WBG_CAS_LAUNCH_POOL(256);
 #undef WBG_CAS_LAUNCH_POOL
-#undef WBG_CAS_LAUNCH_CLASS
 #undef WBG_CAS_LAUNCH_K
     if (model->all_d2) {
         // remember that this stream reads the bank: a later table switch on another stream waits for this event

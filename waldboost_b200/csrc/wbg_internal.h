@@ -46,8 +46,6 @@ struct CascadeGeom {
     int compact_num, compact_den;   // re-pack when alive * den <= slots * num   (num/den <= 1/2)
     int round_full, round_mid, round_tail;   // stages per round while slots > threads / > 64 / else
     int round_n1, round_n2;                  // pool kernel: window counts that separate round_full / round_mid / round_tail
-    int sm_maxnk;                            // depth-2 rounds with <= this many slots per thread read stage records from smem
-    int spec_n;                              // depth-2: speculative rounds once <= this many windows are left (0 = off)
     int pack;                                // slots per thread after a re-pack (0 = keep one slot column per thread)
 };
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g);
@@ -103,17 +101,6 @@ struct __align__(16) StageD2 {
 };
 constexpr int D2_MAX_STAGES = 1280;  // 61,440 bytes of __constant__
 
-// The same stage laid out for the shared-memory copy that the sparse rounds read (three 16-byte groups: root, left
-// child, right child): a warp with few windows is bound by the latency of the stage record, and a broadcast LDS.128 has
-// a fixed ~30-cycle latency where an indexed constant load misses the small constant cache once per stage.
-struct __align__(16) StageD2S {
-    int off0; float thr0, theta, pad_;     // root: byte offset of the feature inside the planar patch, threshold; stage theta
-    int offL; float thrL, pLL, pLR;        // left child (taken when x0 <= thr0) and its two leaves
-    int offR; float thrR, pRL, pRR;        // right child and its two leaves
-};
-static_assert(sizeof(StageD2S) == 48, "StageD2S layout");
-constexpr int D2S_ROUND_MAX = 128;   // stages per round whose records are staged in shared memory (6 KB)
-
 // One stage as a COMPLETE depth-4 tree in heap order (node i -> children 2i+1, 2i+2) for trees of depth <= 4 that are
 // not canonical depth-2 stages: 15 internal nodes, 16 leaves.  A leaf of the original tree that sits higher up is
 // expanded into a subtree whose internal nodes always go left (threshold +inf) and whose leaves all carry its value.
@@ -140,7 +127,6 @@ struct wbg_model {
     float* d_theta = nullptr;
     NodeDev* d_nodes = nullptr;   // [T][N]
     StageD2* d_d2 = nullptr;      // [T] when all_d2
-    StageD2S* d_d2s = nullptr;    // [T] when all_d2: the layout staged in shared memory per round
     bool all_dk4 = false;         // every stage fits a complete depth-4 tree (and the model is not all_d2)
     StageDK4* d_dk4 = nullptr;    // [T] when all_dk4
 };
