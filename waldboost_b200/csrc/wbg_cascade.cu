@@ -34,6 +34,8 @@
 
 __constant__ StageD2 c_d2[D2_MAX_STAGES];
 
+constexpr int WBG_DBG_TILES = 16384;     // tiles covered by the per-tile debug log
+
 struct CascadeParams {
     const float* chns;
     long long chn_stride;
@@ -299,15 +301,35 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
     const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;
     const int pitch = p.pitch, plane = p.plane;
     if (tid < 2) s_tail[tid] = 0;
+    const long long dbg_t0 = p.dbg ? clock64() : 0;
 
     // ---- stage the channel patch, HWC in HBM -> planar in shared memory
     const float* __restrict__ src = p.chns + (long long)frame * p.chn_stride + chn_off + ((long long)r0 * v + c0) * p.C;
     if (p.C == 4) {
-        for (int i = tid; i < lrows * lcols; i += THREADS) {
-            const int rr = i / lcols, cc = i - rr * lcols;
-            const float4 x = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * v + cc) * 4));
-            float* d = tile + rr * pitch + cc;
-            d[0] = x.x; d[plane] = x.y; d[2 * plane] = x.z; d[3 * plane] = x.w;
+        // four 16-byte loads in flight per thread before the first store: the patch costs about two HBM round trips
+        // instead of one per pixel of the thread
+        constexpr int SU = 4;
+        const int total = lrows * lcols;
+        for (int i0 = tid; i0 < total; i0 += SU * THREADS) {
+            float4 x[SU];
+            int off[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int i = i0 + u * THREADS;
+                off[u] = -1;
+                if (i < total) {
+                    const int rr = i / lcols, cc = i - rr * lcols;
+                    x[u] = __ldg(reinterpret_cast<const float4*>(src + ((long long)rr * v + cc) * 4));
+                    off[u] = rr * pitch + cc;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                if (off[u] >= 0) {
+                    float* d = tile + off[u];
+                    d[0] = x[u].x; d[plane] = x[u].y; d[2 * plane] = x[u].z; d[3 * plane] = x[u].w;
+                }
+            }
         }
     } else {
         for (int i = tid; i < lrows * lcols; i += THREADS) {
@@ -453,6 +475,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
     if (p.dbg) {
         if (lane == 0 && w) atomicAdd(p.dbg + 4, (unsigned long long)w);
         if (tid == 0) atomicAdd(p.dbg + 7, 1ull);
+        // per-tile log (first WBG_DBG_TILES tiles): lifetime of the warp that leaves last, windows entering stages
+        if (blockIdx.x < WBG_DBG_TILES) {
+            if (lane == 0) atomicMax(p.dbg + 16 + 2 * blockIdx.x, (unsigned long long)(clock64() - dbg_t0));
+            if (lane == 0 && w) atomicAdd(p.dbg + 17 + 2 * blockIdx.x, (unsigned long long)w);
+        }
     }
 }
 
@@ -614,8 +641,8 @@ static unsigned long long* wbg_debug_counters_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= WBG_MAX_DEVICES) return nullptr;
     if (!g_dbg_dev[dev]) {
-        if (cudaMalloc(&g_dbg_dev[dev], 16 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        cudaMemset(g_dbg_dev[dev], 0, 16 * sizeof(unsigned long long));
+        if (cudaMalloc(&g_dbg_dev[dev], (16 + 2 * WBG_DBG_TILES) * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(g_dbg_dev[dev], 0, (16 + 2 * WBG_DBG_TILES) * sizeof(unsigned long long));
     }
     return g_dbg_dev[dev];
 }
@@ -623,9 +650,17 @@ extern "C" int wbg_cascade_counters_enable(int32_t on) {
     if (on) {
         unsigned long long* d = wbg_debug_counters_device();
         WBG_REQUIRE(d, "wbg_cascade_counters_enable: no CUDA device");
-        WBG_CUDA_TRY(cudaMemset(d, 0, 16 * sizeof(unsigned long long)));
+        WBG_CUDA_TRY(cudaMemset(d, 0, (16 + 2 * WBG_DBG_TILES) * sizeof(unsigned long long)));
     }
     g_dbg_on.store(on != 0);
+    return WBG_OK;
+}
+// (debug aid, not part of wbg.h) per-tile log of the launches since enable(1): pairs {lifetime in cycles, n_weak}
+extern "C" int wbg_cascade_tile_log(uint64_t* out, int64_t n_tiles) {
+    WBG_REQUIRE(out && n_tiles >= 0 && n_tiles <= WBG_DBG_TILES, "wbg_cascade_tile_log: bad argument");
+    unsigned long long* d = wbg_debug_counters_device();
+    WBG_REQUIRE(d, "wbg_cascade_tile_log: no CUDA device");
+    WBG_CUDA_TRY(cudaMemcpy(out, d + 16, 2 * (size_t)n_tiles * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return WBG_OK;
 }
 extern "C" int wbg_cascade_counters_read(uint64_t* out16) {
