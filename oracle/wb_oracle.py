@@ -440,6 +440,27 @@ class Cascade:
         return H, mask
 
 
+def detect_multi(image, cascades, channel_opts=None, response_scale=None):
+    """waldboost.detect(image, *models, channel_opts=, response_scale=) -- __init__.py:75-130: one pyramid shared by all
+    models; per level every model's predict_on_image; scores times response_scale[k]; label = model index.
+    -> (boxes [K,4] f32, scores [K] f32, label [K] i64) in the order of the reference's loops (level, model, r, c)."""
+    channel_opts = channel_opts or cascades[0].channel_opts
+    if response_scale is None:
+        response_scale = [1] * len(cascades)
+    response_scale = np.array(response_scale, "f")
+    if response_scale.size != len(cascades):
+        raise ValueError("Wrong response_scale parameter")
+    B, S, L = [np.empty((0, 4), F32)], [np.empty(0, F32)], [np.empty(0, np.int64)]
+    for chns, scale in channel_pyramid(image, channel_opts):
+        for k, Cs in enumerate(cascades):
+            r, c, h = Cs.predict_on_image(chns)
+            if r.size > 0:                                   # __init__.py:125
+                B.append(Cs.get_boxes(r, c, scale))
+                S.append(h * response_scale[k])
+                L.append(np.full(r.size, k, np.int64))
+    return np.concatenate(B, axis=0), np.concatenate(S), np.concatenate(L)
+
+
 def gather_samples(chns, rs, cs, shape):
     """samples.py:14-43."""
     if rs.size != cs.size:

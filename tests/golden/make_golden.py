@@ -11,6 +11,14 @@ Outputs (all small, committed):
   configA_detect.npz   reference Model.detect on the 640x480 config-A frame: boxes, scores, n_loc, n_weak,
                        per-level float64 channel sums
   generic_model.pb     unbalanced / depth-3 trees (generic-topology path) + reference outputs in generic_detect.npz
+  configB_model.pb / configB_detect.npz   (--config-b)  the model bench.py times + reference detect() on a 540x960 crop
+  fpga_pyramid.npz     (--fpga)      integer channels of the reference's FPGA variant
+  multi_*.pb / multi_detect.npz      (--multi)     waldboost.detect(image, A, B, response_scale=...) of the reference:
+                       boxes, scores, labels in the reference's order (__init__.py:75-130)
+  configC_model.pb / configC_detect.npz  (--config-c)  one 3840x2160 frame, 20x20x10 grad_mag + grad_hist(9) channels,
+                       256 depth-2 stages: the reference's detect() at BASELINE config C's stated size
+  configD_model.pb / configD_scan.npz    (--config-d)  a 2048-stage depth-4 cascade through the reference's
+                       Model.scan_channels (the dense-scoring call of Pool.update, BASELINE config D)
 """
 import os
 import sys
@@ -43,7 +51,7 @@ def ref_model(shape, opts, trees, thetas):
     return M
 
 
-def calibrate(M, chns_list, T, keep_total, subsample=None, seed=0):
+def calibrate(M, chns_list, T, keep_total, subsample=None, seed=0, recipe=None):
     """wald thetas from the reference's own DTree.predict_on_image over all windows of the given maps
     (or a seeded random fraction `subsample` of them)."""
     m, n, _ = M.shape
@@ -66,7 +74,7 @@ def calibrate(M, chns_list, T, keep_total, subsample=None, seed=0):
             sel = mp[idx] == k
             out[sel] = M.classifier[t].predict_on_image(X, R[idx][sel], Cc[idx][sel])
         return out
-    return S.calibrate_thetas(stage, T, keep_total)
+    return (recipe or S.calibrate_thetas)(stage, T, keep_total)
 
 
 def detect_record(M, image):
@@ -131,6 +139,89 @@ def fpga_pyramid():
     print("fpga fixtures:", len(out))
 
 
+def multi_model():
+    """waldboost.detect(image, A, B, response_scale=[1.0, 0.5]) of the reference (__init__.py:75-130): one shared
+    pyramid, two models of different window sizes, scores scaled per model, `label` = model index; the output order is
+    (level, model, r, c).  ref_harness restores the `np.int` alias that __init__.py:128 still names."""
+    frame = S.synthetic_frame(1000, 200, 260)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=rch.grad_hist)
+    lv = list(rch.channel_pyramid(frame, opts))
+    lo, hi = S.channel_quantiles(lv[0][0])
+    models = []
+    for name, shape, seed in (("A", (12, 12, 4), 1), ("B", (16, 10, 4), 2)):
+        trees = S.random_trees(shape, 16, 2, lo, hi, seed=seed)
+        M = ref_model(shape, opts, trees, [-np.inf] * 16)
+        M.theta = [float(x) for x in calibrate(M, [lv[0][0]], 16, 1e-2)]
+        M.save(os.path.join(HERE, f"multi_{name}_model.pb"))
+        models.append(RModel.load(os.path.join(HERE, f"multi_{name}_model.pb")))
+    dt = wb.detect(frame, *models, response_scale=[1.0, 0.5])
+    one = [m.detect(frame) for m in models]
+    np.savez_compressed(os.path.join(HERE, "multi_detect.npz"), boxes=dt.get(), scores=dt.get_field("scores"),
+                        label=np.asarray(dt.get_field("label"), np.int64),
+                        boxes_A=one[0].get(), scores_A=one[0].get_field("scores"),
+                        boxes_B=one[1].get(), scores_B=one[1].get_field("scores"))
+    print("multi-model: hits", len(dt), "labels", np.bincount(np.asarray(dt.get_field("label"), np.int64)))
+
+
+def _mag_hist(im):
+    """config C's 10-channel feature: the concatenation of the reference's own two functions on the same image."""
+    return np.concatenate([rch.grad_mag(im), rch.grad_hist(im, 9)], axis=-1)
+
+
+def config_C():
+    """BASELINE config C at its stated size: one 3840x2160 uint8 frame, 20x20x10 model (grad_mag + 9-bin grad_hist,
+    shrink 2, n_per_oct 8, smooth 1), 256 depth-2 stages with wald thetas calibrated by the reference on a seeded 2 %
+    sample of the windows of every level.  Minutes of CPU."""
+    import waldboost_b200 as wbp
+    shape = (20, 20, 10)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=_mag_hist)
+    frame = S.synthetic_frame(1000, 2160, 3840)
+    lv = [c for c, _ in rch.channel_pyramid(frame, opts) if c.shape[0] > 20 and c.shape[1] > 20]
+    lo, hi = S.channel_quantiles(lv[0])
+    trees = S.random_trees(shape, 256, 2, lo, hi, seed=7)
+    M = ref_model(shape, opts, trees, [-np.inf] * 256)
+    th = calibrate(M, lv, 256, 1e-4, subsample=0.02, seed=1)
+    M.theta = [float(x) for x in th]
+    # the model file is written by the product package (the reference cannot name a lambda as channel function)
+    P = wbp.Model(shape, dict(shrink=2, n_per_oct=8, smooth=1, channels=wbp.channels.grad_mag_hist))
+    for t, thv in zip(trees, th):
+        P.append(t, float(np.float32(thv)))
+    P.save(os.path.join(HERE, "configC_model.pb"))
+    P = wbp.Model.load(os.path.join(HERE, "configC_model.pb"))
+    M = ref_model(shape, opts, P.classifier, P.theta)          # float32-exact thresholds and thetas on both sides
+    levels, boxes, scores, n_loc, n_weak = detect_record(M, frame)
+    np.savez_compressed(os.path.join(HERE, "configC_detect.npz"), boxes=boxes, scores=scores, n_loc=np.int64(n_loc),
+                        n_weak=np.int64(n_weak), level_counts=np.array([r.size for r, *_ in levels]))
+    print("config C (3840x2160): hits", scores.size, "n_loc", n_loc, "n_weak", n_weak, "eval_cost", n_weak / n_loc)
+
+
+def config_D():
+    """BASELINE config D's cascade shape at full length: 2048 depth-4 stages (12x12x4 grad_hist) through the reference's
+    Model.scan_channels on one 200x260 frame -- per level the surviving (r, c, h)."""
+    shape = (12, 12, 4)
+    opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=rch.grad_hist)
+    frame = S.synthetic_frame(1003, 200, 260)
+    lv = [c for c, _ in rch.channel_pyramid(frame, opts) if c.shape[0] > 12 and c.shape[1] > 12]
+    lo, hi = S.channel_quantiles(lv[0])
+    trees = S.random_trees(shape, 2048, 4, lo, hi, seed=7)
+    M = ref_model(shape, opts, trees, [-np.inf] * 2048)
+    th = calibrate(M, lv[:4], 2048, 1e-3)
+    M.theta = [float(x) for x in th]
+    M.save(os.path.join(HERE, "configD_model.pb"))
+    M = RModel.load(os.path.join(HERE, "configD_model.pb"))
+    M.reset()
+    rec = {}
+    k = 0
+    for k, (chns, scale, (r, c, h)) in enumerate(M.scan_channels(frame)):
+        rec[f"{k}/r"], rec[f"{k}/c"], rec[f"{k}/h"] = r.astype(np.int32), c.astype(np.int32), h
+        rec[f"{k}/scale"] = np.float64(scale)
+    rec["n_levels"] = np.int64(k + 1)
+    rec["n_loc"], rec["n_weak"] = np.int64(M.n_loc), np.int64(M.n_weak)
+    np.savez_compressed(os.path.join(HERE, "configD_scan.npz"), **rec)
+    print("config D (2048 x depth 4): levels", k + 1, "survivors", sum(rec[f"{i}/r"].size for i in range(k + 1)),
+          "n_loc", M.n_loc, "n_weak", M.n_weak, "eval_cost", M.n_weak / M.n_loc)
+
+
 def main():
     if "--fpga" in sys.argv:
         return fpga_pyramid()
@@ -138,6 +229,12 @@ def main():
         return config_B()
     if "--config-b-detect" in sys.argv:
         return config_B_detect()
+    if "--multi" in sys.argv:
+        return multi_model()
+    if "--config-c" in sys.argv:
+        return config_C()
+    if "--config-d" in sys.argv:
+        return config_D()
     # ---------------------------------------------------------------- small pyramid fixtures
     frame = S.synthetic_frame(1000, 96, 128)
     frame_f = frame.astype(np.float32) + np.random.default_rng(5).random(frame.shape).astype(np.float32)
@@ -162,7 +259,7 @@ def main():
     lo, hi = S.channel_quantiles(lv[0][0])
     trees = S.random_trees(shape, 24, 2, lo, hi, seed=7)
     M = ref_model(shape, opts, trees, [-np.inf] * 24)
-    th = calibrate(M, [lv[0][0], lv[1][0]], 24, 1e-2)
+    th = calibrate(M, [lv[0][0], lv[1][0]], 24, 1e-2, recipe=S.calibrate_thetas_v0)
     M.theta = [float(x) for x in th]
     M.save(os.path.join(HERE, "small_model.pb"))
     M = RModel.load(os.path.join(HERE, "small_model.pb"))
@@ -193,7 +290,7 @@ def main():
     order = rng.permutation(len(gtrees))
     gtrees = [gtrees[i] for i in order]
     G = ref_model(shape, opts, gtrees, [-np.inf] * len(gtrees))
-    gth = calibrate(G, [lv[0][0]], len(gtrees), 3e-2)
+    gth = calibrate(G, [lv[0][0]], len(gtrees), 3e-2, recipe=S.calibrate_thetas_v0)
     gth[::4] = -np.inf
     G.theta = [float(x) for x in gth]
     G.save(os.path.join(HERE, "generic_model.pb"))
@@ -208,7 +305,7 @@ def main():
     loA, hiA = S.channel_quantiles(lvA[0][0])
     treesA = S.random_trees(shape, 256, 2, loA, hiA, seed=7)
     MA = ref_model(shape, optsA, treesA, [-np.inf] * 256)
-    thA = calibrate(MA, [lvA[0][0]], 256, 1e-4)
+    thA = calibrate(MA, [lvA[0][0]], 256, 1e-4, recipe=S.calibrate_thetas_v0)
     MA.theta = [float(x) for x in thA]
     MA.save(os.path.join(HERE, "configA_model.pb"))
     MA = RModel.load(os.path.join(HERE, "configA_model.pb"))

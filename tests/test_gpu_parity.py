@@ -338,6 +338,25 @@ def test_multi_model_detect_shared_pyramid():
     assert np.array_equal(np.sort(dt.get_field("scores")[lab == 1]), np.sort(b.get_field("scores") * np.float32(0.5)))
 
 
+def test_multi_model_detect_vs_reference_golden():
+    """wb.detect(image, A, B, response_scale=[1, .5]) against the reference's own output (__init__.py:75-130): boxes,
+    scores and labels in the reference's order (level, model, r, c), and the oracle's detect_multi on the same input."""
+    g = np.load(os.path.join(GOLDEN, "multi_detect.npz"))
+    A = wb.Model.load(os.path.join(GOLDEN, "multi_A_model.pb"))
+    B = wb.Model.load(os.path.join(GOLDEN, "multi_B_model.pb"))
+    frame = S.synthetic_frame(1000, 200, 260)
+    dt = wb.detect(frame, A, B, response_scale=[1.0, 0.5])
+    assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+    assert np.array_equal(np.asarray(dt.get_field("label"), np.int64), g["label"])
+    ob, os_, ol = O.detect_multi(frame, [oracle_cascade(A), oracle_cascade(B)], response_scale=[1.0, 0.5])
+    assert np.array_equal(dt.get(), ob) and np.array_equal(dt.get_field("scores"), os_) and np.array_equal(g["label"], ol)
+    a = A.detect(frame)
+    assert np.array_equal(a.get(), g["boxes_A"]) and np.array_equal(a.get_field("scores"), g["scores_A"])
+    # alternating models on one stream re-loads the constant-bank table in stream order (no host synchronisation)
+    for _ in range(3):
+        assert np.array_equal(A.detect(frame).get(), g["boxes_A"]) and np.array_equal(B.detect(frame).get(), g["boxes_B"])
+
+
 def test_model_mutation_resyncs_device_copy():
     frame = S.synthetic_frame(1000, 96, 128)
     M = make_model((12, 12, 4), OPTS_A, 12, 2, frame)
@@ -389,8 +408,19 @@ def test_level_subset_equals_filtered_full_detect():
     assert np.array_equal(one.get_field("scores"), full["score"][full["level"] == 2])
 
 
+def _hit_diff(got_boxes, got_scores, ref_boxes, ref_scores):
+    """hits keyed by box: (missing from got, extra in got, common with a different score)."""
+    got = {tuple(b): s for b, s in zip(map(tuple, got_boxes), got_scores)}
+    ref = {tuple(b): s for b, s in zip(map(tuple, ref_boxes), ref_scores)}
+    missing = [k for k in ref if k not in got]
+    extra = [k for k in got if k not in ref]
+    moved = [k for k in ref if k in got and got[k] != ref[k]]
+    return missing, extra, moved
+
+
 def test_config_C_shape_mag_hist_20x20x10():
-    """config C's model shape (20x20 window, 10 channels = grad_mag + 9-bin grad_hist) end to end vs the oracle."""
+    """config C's model shape (20x20 window, 10 channels = grad_mag + 9-bin grad_hist) end to end vs the oracle: the
+    hit list is the oracle's, bit for bit (grad_mag's float32 sqrt / division chain included)."""
     frame = S.synthetic_frame(1002, 360, 640)
     opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=CH.grad_mag_hist)
     M = make_model((20, 20, 10), opts, 48, 2, frame, keep_total=1e-2, calib_levels=2)
@@ -398,14 +428,25 @@ def test_config_C_shape_mag_hist_20x20x10():
     M.reset()
     dt = M.detect(frame)
     boxes, scores, _ = Cs.detect(frame)
-    agree = np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
-    if not agree:      # grad_mag's division / sqrt chain is float32 on both sides; tolerate isolated last-ulp effects
-        got = {tuple(b): s for b, s in zip(map(tuple, dt.get()), dt.get_field("scores"))}
-        ref = {tuple(b): s for b, s in zip(map(tuple, boxes), scores)}
-        union = set(got) | set(ref)
-        good = sum(1 for k in union if k in got and k in ref and abs(got[k] - ref[k]) <= 1e-4)
-        assert good / len(union) >= 0.95
-    assert M.n_loc == Cs.n_loc and scores.size > 0
+    missing, extra, moved = _hit_diff(dt.get(), dt.get_field("scores"), boxes, scores)
+    assert (len(missing), len(extra), len(moved)) == (0, 0, 0), (len(missing), len(extra), len(moved), scores.size)
+    assert np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
+    assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak) and scores.size > 0
+
+
+def test_config_C_4k_vs_reference_golden():
+    """BASELINE config C at its stated size: one 3840x2160 frame, 20x20x10 grad_mag + grad_hist(9), 256 stages, against
+    the reference's own detect() output (tests/golden/make_golden.py --config-c): 12,324,184 windows, bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "configC_detect.npz"))
+    M = wb.Model.load(os.path.join(GOLDEN, "configC_model.pb"))
+    assert len(M) == 256 and tuple(M.shape) == (20, 20, 10)
+    frame = S.synthetic_frame(1000, 2160, 3840)
+    M.reset()
+    dt = M.detect(frame)
+    missing, extra, moved = _hit_diff(dt.get(), dt.get_field("scores"), g["boxes"], g["scores"])
+    assert (len(missing), len(extra), len(moved)) == (0, 0, 0), (len(missing), len(extra), len(moved), g["scores"].size)
+    assert np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+    assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"])) and M.n_loc == 12324184
 
 
 def test_config_D_shape_depth4_scan_batch():
@@ -420,6 +461,29 @@ def test_config_D_shape_depth4_scan_batch():
         h = hits[hits["frame"] == b]
         assert np.array_equal(h["score"], sc) and np.array_equal(h["level"], lv) and np.array_equal(out[b].get(), bx)
     assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak) and hits.size > 0
+
+
+def test_config_D_2048_depth4_scan_vs_reference_golden():
+    """BASELINE config D's cascade at full length (2048 depth-4 stages) through scan_channels, against the
+    reference's own per-level survivors (tests/golden/make_golden.py --config-d)."""
+    g = np.load(os.path.join(GOLDEN, "configD_scan.npz"))
+    M = wb.Model.load(os.path.join(GOLDEN, "configD_model.pb"))
+    assert len(M) == 2048
+    frame = S.synthetic_frame(1003, 200, 260)
+    M.reset()
+    n = 0
+    for k, (chns, scale, (r, c, h)) in enumerate(M.scan_channels(frame)):
+        assert scale == float(g[f"{k}/scale"])
+        assert np.array_equal(r, g[f"{k}/r"]) and np.array_equal(c, g[f"{k}/c"]) and np.array_equal(h, g[f"{k}/h"])
+        n += r.size
+    assert k + 1 == int(g["n_levels"]) and n > 0
+    assert (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))
+    # the same cascade as a dense-scoring batch (Pool.update pattern): every frame equals its single-frame result
+    frames = np.stack([frame, S.synthetic_frame(1004, 200, 260), frame])
+    M.reset()
+    out, hits = M.detect_batch(frames, return_hits=True)
+    assert np.array_equal(hits[hits["frame"] == 0]["score"], hits[hits["frame"] == 2]["score"])
+    assert np.array_equal(hits[hits["frame"] == 0]["score"], np.concatenate([g[f"{i}/h"] for i in range(k + 1)]))
 
 
 def test_sample_mode_predict():
@@ -543,8 +607,17 @@ def test_randomised_shapes_and_options_vs_oracle(seed):
     if exact_channels:
         assert np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
         assert (M.n_loc, M.n_weak) == (Cs.n_loc, Cs.n_weak)
-    else:                                            # float32 frames / grad_mag: channels within 1e-5, hits may flip at a threshold
-        assert M.n_loc == Cs.n_loc and abs(len(dt) - scores.size) <= max(2, 0.05 * scores.size)
+    else:
+        # float32 frames / grad_mag: channels within 1e-5 but not bit-equal, so a window whose feature sits within that
+        # distance of a threshold may take the other branch.  SURVEY.md 8d gate: hits matched by box, |score| within
+        # 1e-4, agreement >= 95 % of the union; the counts are asserted, not just the length of the hit list.
+        missing, extra, moved = _hit_diff(dt.get(), dt.get_field("scores"), boxes, scores)
+        got = {tuple(b): s for b, s in zip(map(tuple, dt.get()), dt.get_field("scores"))}
+        ref = {tuple(b): s for b, s in zip(map(tuple, boxes), scores)}
+        far = [k for k in moved if abs(float(got[k]) - float(ref[k])) > 1e-4]
+        union = len(ref) + len(extra)
+        assert M.n_loc == Cs.n_loc
+        assert len(missing) + len(extra) + len(far) <= max(2, 0.05 * union), (len(missing), len(extra), len(far), union)
 
 
 def test_detect_input_edge_cases():

@@ -240,3 +240,39 @@ def test_oracle_fpga_channels_equal_reference_golden(name, tag):
         ref = g[f"{name}/{tag}/{k}"]
         assert chns.dtype == np.uint8 == ref.dtype and np.array_equal(chns, ref), f"level {k}"
         assert scale == float(g[f"{name}/{tag}/{k}/scale"])
+
+
+# ------------------------------------------------------------------------------------- goldens added in round 2
+def _load_cascade(path):
+    """reference-written .pb -> oracle Cascade (host-side parsing by the product package's wire-format mirror)."""
+    import waldboost_b200 as wb
+    return O.cascade_from_model(wb.Model.load(path))
+
+
+def test_multi_model_detect_vs_reference_golden():
+    """waldboost.detect(image, A, B, response_scale=[1, .5]) of the reference: boxes, scores and labels in its order."""
+    from waldboost_b200 import synthetic as S
+    g = np.load(os.path.join(GOLDEN, "multi_detect.npz"))
+    A, B = _load_cascade(os.path.join(GOLDEN, "multi_A_model.pb")), _load_cascade(os.path.join(GOLDEN, "multi_B_model.pb"))
+    frame = S.synthetic_frame(1000, 200, 260)
+    boxes, scores, label = O.detect_multi(frame, [A, B], response_scale=[1.0, 0.5])
+    assert np.array_equal(boxes, g["boxes"]) and np.array_equal(scores, g["scores"]) and np.array_equal(label, g["label"])
+    assert (label == 0).sum() > 0 and (label == 1).sum() > 0
+    ba, sa, _ = A.detect(frame)
+    assert np.array_equal(ba, g["boxes_A"]) and np.array_equal(sa, g["scores_A"])
+
+
+def test_config_D_2048_depth4_scan_vs_reference_golden():
+    """2048 depth-4 stages through scan_channels (BASELINE config D's cascade at full length)."""
+    from waldboost_b200 import synthetic as S
+    g = np.load(os.path.join(GOLDEN, "configD_scan.npz"))
+    Cs = _load_cascade(os.path.join(GOLDEN, "configD_model.pb"))
+    assert len(Cs) == 2048 and all(len(w.left) == 31 for w in Cs.classifier)
+    frame = S.synthetic_frame(1003, 200, 260)
+    n = 0
+    for k, (chns, scale, (r, c, h)) in enumerate(Cs.scan_channels(frame)):
+        assert scale == float(g[f"{k}/scale"])
+        assert np.array_equal(r, g[f"{k}/r"]) and np.array_equal(c, g[f"{k}/c"]) and np.array_equal(h, g[f"{k}/h"])
+        n += r.size
+    assert k + 1 == int(g["n_levels"]) and n > 0
+    assert (Cs.n_loc, Cs.n_weak) == (int(g["n_loc"]), int(g["n_weak"]))

@@ -85,6 +85,13 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+// the same load for data that is rewritten between rounds (the staged stage records of the depth-4 path): volatile, so
+// the compiler neither merges it across rounds nor hoists it above the barrier that follows the staging
+__device__ __forceinline__ float lds_f32v(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 // 8-byte variant; volatile because the staged stage records it reads are rewritten every round
 __device__ __forceinline__ float2 lds_v2(unsigned addr) {
     float2 v;
@@ -135,7 +142,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
         for (int s = t; s < t_end; ++s) {
             const unsigned rec = rec_base + (unsigned)(s - t) * (unsigned)sizeof(StageDK4);
             const float2 root = lds_v2(rec);
-            const float theta = lds_f32(rec + 120u);
+            const float theta = lds_f32v(rec + 120u);
             unsigned nd_addr[NK];                   // address of the current node record; node i sits at rec + 8 i
 #pragma unroll
             for (int k = 0; k < NK; ++k)
@@ -153,7 +160,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
             for (int k = 0; k < NK; ++k) {
                 entered[k] += alive[k];
                 // leaf j = i - 15 is the float at rec + 128 + 4 j, and nd_addr = rec + 8 i
-                hs[k] += lds_f32(rec + 128u + ((nd_addr[k] - rec) >> 1) - 60u);     // float32 accumulation in stage order (model.py:251)
+                hs[k] += lds_f32v(rec + 128u + ((nd_addr[k] - rec) >> 1) - 60u);     // float32 accumulation in stage order (model.py:251)
                 alive[k] *= fset_ge(hs[k], theta);                                  // model.py:255
             }
         }
@@ -724,9 +731,12 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     const CascadeGeom& g = model->geom;
     p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
-    const bool use_dk4 = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
+    const bool use_dk4_req = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
     p.rec_off = (g.smem_bytes + 15) & ~15;
     // dynamic shared memory: patch | survivor pool | stage records of a round (depth-4 path)
+    // the depth-4 path adds its staged records to the tile; a tile that then no longer fits the opt-in limit of an SM falls
+    // back to the node-record traversal instead of failing at launch
+    bool use_dk4 = use_dk4_req && p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4) <= 227 * 1024;
     const int smem = use_dk4 ? p.rec_off + DK4_ROUND_MAX * (int)sizeof(StageDK4) : g.smem_bytes;
     // The depth-2 stage table lives in the constant bank, which is one per device.  Loading it is ordered with
     // events, never with a host-side wait: the copy is enqueued on the launching stream after that stream has been

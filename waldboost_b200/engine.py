@@ -150,6 +150,19 @@ class ModelHandle:
             pass
 
 
+def _check_windows(rs, cs, u, v, m, n):
+    """Window origins for the explicit-window entry points.  The reference gathers X[rs + r, cs + c] with NumPy fancy
+    indexing (training.py:92, samples.py:14-43): an origin whose window leaves the map raises IndexError there, and the
+    device kernels do not bounds-check, so the same error is raised here before anything is launched."""
+    rs = np.ascontiguousarray(rs, np.int64).ravel()
+    cs = np.ascontiguousarray(cs, np.int64).ravel()
+    if rs.size != cs.size:
+        raise ValueError("Sizes of 'rs' and 'cs' must match")
+    if rs.size and (rs.min() < 0 or cs.min() < 0 or rs.max() + m > u or cs.max() + n > v):
+        raise IndexError(f"window origin outside the {u} x {v} channel map for a {m} x {n} window")
+    return rs.astype(np.int32), cs.astype(np.int32)
+
+
 class Engine:
     def __init__(self, device_index):
         torch = _torch()
@@ -346,11 +359,11 @@ class Engine:
                 chns = self.pyramid(dev, plan, slot=slot)
                 cap = self.default_hit_cap(plan, n)
                 hits_t, meta, nbytes = self.cascade_launch(model_handle, plan, chns, n, cap, slot)
-                host_meta = self.pinned("meta%d" % i, nbytes)
+                host_meta = self.pinned("meta" + slot, nbytes)        # two slots: chunk i-1 is read before chunk i+1 is issued
                 host_meta[:nbytes].copy_(meta[:nbytes], non_blocking=True)
                 # the hit list is small in practice: copy an optimistic prefix right away, the rest on demand
                 pre = min(cap, 4096) * N.HIT_DTYPE.itemsize
-                host_hits = self.pinned("hits%d" % i, pre)
+                host_hits = self.pinned("hits" + slot, pre)
                 host_hits[:pre].copy_(hits_t[:pre], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -421,9 +434,11 @@ class Engine:
     def trace(self, model_handle, X, rs, cs):
         """(leaf [K,T] uint8, score [K] float32) for explicit windows, no rejection (wbg_cascade_trace)."""
         torch = self.torch
-        Xd = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
-        rs_d = torch.from_numpy(np.ascontiguousarray(rs, np.int32)).to(self.device)
-        cs_d = torch.from_numpy(np.ascontiguousarray(cs, np.int32)).to(self.device)
+        X = np.ascontiguousarray(X, np.float32)
+        rs, cs = _check_windows(rs, cs, X.shape[0], X.shape[1], model_handle.shape[0], model_handle.shape[1])
+        Xd = torch.from_numpy(X).to(self.device)
+        rs_d = torch.from_numpy(rs).to(self.device)
+        cs_d = torch.from_numpy(cs).to(self.device)
         K, T = int(rs_d.numel()), model_handle.T
         leaf = torch.zeros((K, max(T, 1)), dtype=torch.uint8, device=self.device)
         score = torch.zeros(K, dtype=torch.float32, device=self.device)
@@ -448,10 +463,12 @@ class Engine:
     def gather_samples(self, X, rs, cs, shape):
         torch = self.torch
         m, n = int(shape[0]), int(shape[1])
-        Xd = torch.from_numpy(np.ascontiguousarray(X, np.float32)).to(self.device)
+        X = np.ascontiguousarray(X, np.float32)
+        rs, cs = _check_windows(rs, cs, X.shape[0], X.shape[1], m, n)
+        Xd = torch.from_numpy(X).to(self.device)
         ch = int(Xd.shape[2])
-        rs_d = torch.from_numpy(np.ascontiguousarray(rs, np.int32)).to(self.device)
-        cs_d = torch.from_numpy(np.ascontiguousarray(cs, np.int32)).to(self.device)
+        rs_d = torch.from_numpy(rs).to(self.device)
+        cs_d = torch.from_numpy(cs).to(self.device)
         K = int(rs_d.numel())
         out = torch.empty((K, m, n, ch), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

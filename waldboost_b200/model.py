@@ -62,6 +62,7 @@ class Model:
         self.reset()
         self._handle = None
         self._handle_key = None
+        self._handle_trees = None
 
     # ------------------------------------------------------------------------------------------- stats
     @property
@@ -97,6 +98,7 @@ class Model:
         """Force a re-upload of the cascade (needed only after mutating a DTree's arrays in place)."""
         self._handle = None
         self._handle_key = None
+        self._handle_trees = None
 
     def _device_model(self):
         """The lists are user-mutable (reference scripts assign model.theta, append stages): re-sync lazily."""
@@ -109,6 +111,9 @@ class Model:
             with eng.torch.cuda.device(eng.device):        # the handle's tables live on the engine's device
                 self._handle = ModelHandle(self.shape, self.classifier, self.theta)
             self._handle_key = key
+            # the key names the trees by id(): keep them alive as long as the key is, so that a tree that replaces a
+            # dropped one (model.classifier.pop(); model.append(DTree(...))) can never be given the same id
+            self._handle_trees = list(self.classifier)
         return self._handle
 
     def _spec(self):

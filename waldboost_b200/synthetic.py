@@ -110,3 +110,27 @@ def calibrate_thetas(stage_scores_fn, n_stages, keep_total=1e-4):
         m = hs >= th
         alive, hs = alive[m], hs[m]
     return thetas
+
+
+def calibrate_thetas_v0(stage_scores_fn, n_stages, keep_total=1e-4):
+    """The first calibration recipe: theta_t = the lower quantile of the running score that keeps the fraction
+    keep_total**(1/T) of the windows ENTERING stage t.  Kept verbatim because tests/golden/small_model.pb,
+    generic_model.pb and configA_model.pb (and the reference outputs recorded with them) were generated with it; ties
+    at the quantile keep more windows than the target, which calibrate_thetas fixes for the larger models."""
+    keep = keep_total ** (1.0 / n_stages)
+    thetas = np.empty(n_stages, np.float32)
+    alive, hs = None, None
+    for t in range(n_stages):
+        pred = stage_scores_fn(t, alive)
+        if hs is None:
+            hs = np.zeros(pred.shape, np.float32)
+            alive = np.arange(pred.size)
+        hs = hs + pred.astype(np.float32)
+        if hs.size == 0:
+            thetas[t] = -np.inf
+            continue
+        th = np.float32(np.quantile(hs, 1.0 - keep, method="lower"))
+        thetas[t] = th
+        m = hs >= th
+        alive, hs = alive[m], hs[m]
+    return thetas
