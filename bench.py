@@ -15,8 +15,9 @@ is used only for the barrier and the max-over-ranks of the step time ("scaling":
             read of the hits inside the timed region.
   roofline  for the kernel with the larger share of the step: ALGORITHMIC bytes per launch / its CUDA-event time;
             `roofline_pyramid` and `roofline_cascade` give both kernels.
-  cpu_baseline  the oracle (a NumPy restatement of the reference's own algorithm, oracle/wb_oracle.py) on the host
-            cores, image-sharded over worker processes, on a bounded sample of the same workload.
+  cpu_baseline  the reference's CPU path on the host cores (oracle/cpu_arm.py): the unmodified reference where
+            /root/reference exists ("kind": "reference"), its NumPy restatement oracle/wb_oracle.py elsewhere ("port"),
+            image-sharded over worker processes on a bounded sample of the same workload, plus a single-core figure.
 
 --impl reference times only that CPU path and prints the same line with "impl": "reference".
 """
@@ -40,26 +41,13 @@ UNIT = "frames/s"
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference path
-CPU_GROUP = 4      # worker processes sharing one frame (its pyramid levels are split between them, largest level = 16 %)
-
-
-def _cpu_worker(job):
-    """One worker process: oracle detect() on the given pyramid levels of one 1080p frame.  The oracle is imported
-    only here (CPU baseline / reference arm)."""
-    seed, levels, profile, h, w = job
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+# Everything the CPU arm runs lives under oracle/ (oracle/cpu_arm.py): the unmodified reference when /root/reference is
+# present (build container), its NumPy restatement otherwise (GPU box).  Neither this arm nor its worker processes import
+# waldboost_b200 or map libwbg.so.
+def _cpu_arm():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import wb_oracle as O  # (checker / CPU baseline only)
-    import waldboost_b200 as wb
-    from waldboost_b200 import synthetic as S
-    M = wb.Model.load(MODEL_B)              # host-side .pb parsing only; no GPU is touched in the worker
-    if profile == "dense":
-        M.theta = [-np.inf] * len(M)
-    Cs = O.cascade_from_model(M)
-    frame = S.synthetic_frame(seed, h, w)
-    t0 = time.perf_counter()
-    hits = Cs.detect(frame, levels)[1].size
-    return time.perf_counter() - t0, hits, Cs.n_loc, Cs.n_weak
+    import cpu_arm   # (checker / CPU baseline only)
+    return cpu_arm
 
 
 def host_cores():
@@ -69,70 +57,60 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-class CpuPool:
-    """Worker processes over frames (the reference's own parallel pattern: multiprocessing.Pool over files,
-    scripts/waldboost-detect.py:65); to keep a step short every frame is additionally split by pyramid level over
-    CPU_GROUP workers (levels are independent, channels.py:125-132).  Spawned, so no CUDA context is inherited."""
+SINGLE_CROP = (270, 810, 480, 1440)     # centre 540x960 of a 1080p frame: the bounded single-thread sample
 
-    def __init__(self, workers):
-        import multiprocessing as mp
-        self.group = min(CPU_GROUP, workers)
-        self.frames = max(1, workers // self.group)
-        self.workers = self.frames * self.group
-        self.pool = mp.get_context("spawn").Pool(self.workers)
 
-    def _level_shards(self, h, w):
-        import waldboost_b200 as wb
-        from waldboost_b200.engine import plan_geometry
-        from waldboost_b200.sharding import assign_levels
-        M = wb.Model.load(MODEL_B)
-        plan = plan_geometry(h, w, M.channel_opts, M._spec(), int(M.shape[0]), int(M.shape[1]))
-        return assign_levels([lv.u * lv.v for lv in plan.levels], self.group)
-
-    def step(self, profile, h=H, w=W, seed0=1000):
-        shards = self._level_shards(h, w)
-        jobs = [(seed0 + f, shards[g], profile, h, w) for f in range(self.frames) for g in range(self.group)]
-        res = self.pool.map(_cpu_worker, jobs, chunksize=1)
-        busy = max(r[0] for r in res)            # slowest worker's detect time (excludes start-up and frame synthesis)
-        return self.frames, busy, sum(r[1] for r in res), sum(r[2] for r in res), sum(r[3] for r in res)
-
-    def sample(self):
-        return (f"{self.frames} frames of 1920x1080 per step on {self.workers} worker processes "
-                f"(each frame's 64 pyramid levels split over {self.group} workers), oracle/wb_oracle.py Cascade.detect")
-
-    def close(self):
-        self.pool.close()
-        self.pool.join()
+def cpu_measure(args, steps, warm):
+    """N-process and single-thread frames/s of the reference's CPU path on a bounded sample of the workload."""
+    A = _cpu_arm()
+    cores = max(1, min(host_cores(), args.cpu_workers or 64))
+    pool = A.CpuPool(cores, MODEL_B, None if args.cpu_kind == "auto" else args.cpu_kind)
+    for _ in range(warm):                        # untimed: a small frame per worker (imports, page-in, JIT if any)
+        pool.step(args.profile, 135, 240)
+    t, frames, n_loc, n_weak = 0.0, 0, 0, 0
+    for _ in range(steps):
+        n, busy, _, nl, nw = pool.step(args.profile, H, W)
+        t += busy; frames += n; n_loc += nl; n_weak += nw
+    single, single_txt = (None, None)
+    if not args.no_single_thread:
+        single, single_txt = pool.single_thread(args.profile, H, W, SINGLE_CROP)
+    sample = pool.sample(H, W)
+    kind, workers = pool.kind, pool.workers
+    pool.close()
+    fps = frames / t
+    return {"value": fps, "unit": UNIT, "cores": workers, "kind": kind,
+            "sample": f"{sample}, {steps} step(s), {n_weak / max(n_loc, 1):.1f} stages per window, {t:.1f} s",
+            "single_thread": {"value": single, "unit": UNIT, "cores": 1, "sample": single_txt}}, t
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on all host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU path on all host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = max(1, min(host_cores(), args.cpu_workers or 10 ** 6))
-    pool = CpuPool(cores)
-    for _ in range(args.warmup):                 # untimed: a small frame per worker (imports, page-in; there is no JIT)
-        pool.step(args.profile, 135, 240)
-    t = 0.0
-    frames = 0
-    for _ in range(args.steps):
-        n, busy, _, _, _ = pool.step(args.profile)
-        t += busy
-        frames += n
-    pool.close()
-    fps = frames / t
+    cpu, t = cpu_measure(args, args.steps, max(args.warmup, 1))
+    fps = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Model.detect, 1920x1080 uint8 frames, 12x12x4 grad_hist model, 1024 depth-2 stages, {args.profile} thetas",
+        "config": {"workload": f"Model.detect, 1920x1080 uint8 frames, 12x12x4 grad_hist model, 1024 depth-2 stages, {args.profile} thetas "
+                               "(BASELINE configs[1]); each step a bounded sample: one frame per worker group",
                    "profile": args.profile},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": pool.workers, "kind": "port",
-                         "sample": pool.sample() + f", {args.steps} steps"},
+        "cpu_baseline": cpu,
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # evidence that this arm is the CPU path only: shared objects of the product mapped into this process
+        "native_so_loaded": _mapped_product_libraries(),
     }
     print(json.dumps(line), flush=True)
+
+
+def _mapped_product_libraries():
+    try:
+        with open("/proc/self/maps") as f:
+            return sorted({l.split()[-1] for l in f if "libwbg" in l})
+    except OSError:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -231,13 +209,7 @@ def run_gpu(args):
     # ---- CPU baseline first (rank 0 at N=1 only), before this process's CUDA work starts: bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = max(1, min(host_cores(), args.cpu_workers or 64))
-        pool = CpuPool(cores)
-        pool.step(args.profile, 135, 240)
-        n_fr, busy, _, n_loc_c, n_weak_c = pool.step(args.profile)
-        pool.close()
-        cpu = {"value": n_fr / busy, "unit": UNIT, "cores": pool.workers, "kind": "port",
-               "sample": pool.sample() + f", eval_cost {n_weak_c / max(n_loc_c, 1):.1f}, {busy:.1f} s"}
+        cpu, _ = cpu_measure(args, 1, 1)
 
     from waldboost_b200.build import build
     if local == 0:
@@ -297,18 +269,45 @@ def run_gpu(args):
     frames_total = B * args.steps * world
     value = frames_total / (ms_total * 1e-3)
 
-    # ---- end to end through the public API: pinned host frames in, boxes out
+    # ---- end to end through the public API: pinned host frames in, boxes out.  With several GPUs the per-rank hit
+    # lists are gathered on the host of rank 0 inside the timed region (north_star: "only a host-side gather of boxes"):
+    # a gloo group next to the NCCL one carries the pickled records, no device collective touches data.
+    from waldboost_b200 import sharding
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def e2e_step(src):
+        out, h = model.detect_batch(src, return_hits=True)
+        h = h.copy()
+        h["frame"] += rank * B                              # global frame indices
+        gathered, stats = sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0)
+        return h, gathered
+
     for _ in range(2):
-        model.detect_batch(frames)
+        e2e_step(frames)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, hits = model.detect_batch(frames, return_hits=True)
+        hits, gathered = e2e_step(frames)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e = {"value": frames_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
-           "d2h_bytes_per_step": int(hits.nbytes + 8 + 16 * B + 4 * B * plan.n_levels)}
+           "d2h_bytes_per_step": int(hits.nbytes + 8 + 16 * B + 4 * B * plan.n_levels),
+           "host_gather": None if world == 1 else f"hit records of {world} ranks gathered on rank 0 (gloo, host memory) inside the timed region: "
+                                                   f"{0 if gathered is None else int(gathered.size)} hits per step"}
+    # the same call on ordinary (pageable) NumPy frames: the library stages them through a page-locked buffer
+    pageable = np.array(frames)
+    e2e_step(pageable)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, args.steps // 3)):
+        e2e_step(pageable)
+    torch.cuda.synchronize()
+    e2e_pg_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e["pageable"] = {"value": B * max(2, args.steps // 3) * world / e2e_pg_s, "unit": UNIT,
+                       "note": "np.ndarray frames that are not page-locked (staged through a pinned buffer by the library)"}
+    del pageable
 
     # ---- roofline of the two dominant kernels (algorithmic bytes per launch / CUDA-event time per launch)
     peaks, peak_src = {}, "fallback 6650 GB/s (B200_PROFILING.md)"
@@ -335,6 +334,7 @@ def run_gpu(args):
         ach = bytes_per_frame * B / per_launch_s / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": (traffic[name]["bytes_per_frame"] * B) if name in traffic else None,
+                "traffic_source": ("profiles/dram_traffic.json: " + traffic[name].get("source", "") + " -- an ncu --set full capture of a 4-frame launch scaled per frame, NOT measured in this run") if name in traffic else None,
                 "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
                 "ms_per_launch": per_launch_s * 1e3, "peak_source": peak_src,
                 # context from the committed ncu capture (profiles/r01_ncu_full_final.csv), not measured in this run:
@@ -381,11 +381,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--unique-frames", type=int, default=16, help="distinct synthetic frames per GPU (cycled to fill the batch)")
+    ap.add_argument("--unique-frames", type=int, default=64, help="distinct synthetic frames per GPU (cycled to fill the batch)")
     ap.add_argument("--profile", choices=["wald", "dense"], default="wald")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-thread", action="store_true", help="skip the single-core sample of the CPU arm")
+    ap.add_argument("--cpu-kind", choices=["auto", "port", "reference"], default="auto",
+                    help="CPU arm: the unmodified reference (needs /root/reference), its NumPy restatement, or whichever is available")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
