@@ -277,9 +277,10 @@ def run_gpu(args):
 
     def e2e_step(src):
         out, h = model.detect_batch(src, return_hits=True)
-        h = h.copy()
-        h["frame"] += rank * B                              # global frame indices
-        gathered, stats = sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0)
+        if world == 1:
+            return h, h
+        h["frame"] += rank * B                              # global frame indices (detect_batch returns a fresh array)
+        gathered, stats = sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0, presorted=True)
         return h, gathered
 
     for _ in range(2):
@@ -375,6 +376,94 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- config C
+MODEL_C = os.path.join(ROOT, "tests", "golden", "configC_model.pb")
+
+
+def run_config_c(args):
+    """BASELINE configs[2]: ONE 3840x2160 frame, 20x20x10 grad_mag + grad_hist(9) model, spread over the GPUs of the box
+    in row bands of pyramid levels (waldboost_b200.sharding.assign_bands), the hit records gathered on the host of rank
+    0.  A step = detect() of that frame through the public API on every rank: H2D of the frame, the rank's bands of the
+    pyramid and of the cascade, D2H of its hits, host gather.  Rank 0 checks the gathered list against the reference's
+    own detect() output (tests/golden/configC_detect.npz)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    host_group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")
+    import waldboost_b200 as wb
+    from waldboost_b200 import sharding, synthetic as S
+    from waldboost_b200.engine import cascade_tile, get_engine, plan_geometry
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = wb.Model.load(MODEL_C)
+    Hc, Wc = 2160, 3840
+    pinned = torch.empty((1, Hc, Wc), dtype=torch.uint8, pin_memory=True)
+    frame = pinned.numpy()
+    frame[0] = S.synthetic_frame(1000, Hc, Wc)
+    m, n, C_ = (int(x) for x in model.shape)
+    plan = plan_geometry(Hc, Wc, model.channel_opts, model._spec(), m, n)
+    TR, _ = cascade_tile(m, n, C_)
+    rows = [(lv.win_rows + TR - 1) // TR if lv.win_rows > 0 and lv.win_cols > 0 else 0 for lv in plan.levels]
+    cost = [TR * lv.v for lv in plan.levels]
+    mine = sharding.assign_bands(rows, cost, world)[rank]
+
+    def step():
+        model.reset()
+        _, h = model.detect_batch(frame, return_hits=True, bands=mine)
+        return sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0)
+
+    for _ in range(max(args.warmup, 3)):
+        hits, stats = step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hits, stats = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    barrier()
+    if rank == 0:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "configC_detect.npz"))
+        boxes = np.stack([hits["x1"], hits["y1"], hits["x2"], hits["y2"]], axis=1)
+        same = bool(np.array_equal(boxes, g["boxes"]) and np.array_equal(hits["score"], g["scores"])
+                    and stats == (int(g["n_loc"]), int(g["n_weak"])))
+        line = {
+            "metric": "3840x2160 frames/sec for Model.detect, one frame spread over the GPUs", "value": args.steps / dt,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single 3840x2160 uint8 frame, 20x20x10 grad_mag + grad_hist(9) model (shrink 2, n_per_oct 8, smooth 1), "
+                                   "256 depth-2 stages, wald thetas (BASELINE configs[2]); pyramid levels split in row bands across the GPUs",
+                       "windows": int(plan.info.n_loc), "levels": plan.n_levels, "bands_rank0": len(mine),
+                       "parallelism": f"(level, row band) x{world}, host gather of hits, no collective on data",
+                       "hits": int(hits.size), "matches_reference_golden": same,
+                       "timed_region": "public API per step on every rank: H2D of the 8.3 MB frame, bands of pyramid + cascade, D2H of hits, gloo gather on rank 0"},
+            "e2e": {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(frame.nbytes) * world,
+                    "d2h_bytes_per_step": int(hits.nbytes)},
+            "gpu_launches": None,
+        }
+        print(json.dumps(line), flush=True)
+        if not same:
+            raise SystemExit("config C: the gathered hit list differs from the reference golden")
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -389,7 +478,11 @@ def main():
     ap.add_argument("--no-single-thread", action="store_true", help="skip the single-core sample of the CPU arm")
     ap.add_argument("--cpu-kind", choices=["auto", "port", "reference"], default="auto",
                     help="CPU arm: the unmodified reference (needs /root/reference), its NumPy restatement, or whichever is available")
+    ap.add_argument("--config", choices=["B", "C"], default="B", help="B: batch of 1080p frames (default, the headline); "
+                    "C: one 3840x2160 frame spread over the GPUs in row bands")
     args = ap.parse_args()
+    if args.config == "C" and args.impl != "reference":
+        return run_config_c(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

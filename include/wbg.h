@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WBG_ABI_VERSION 2
+#define WBG_ABI_VERSION 3
 
 enum { WBG_OK = 0, WBG_EINVAL = -1, WBG_ECAP = -2, WBG_ECUDA = -3, WBG_ENOMEM = -4 };
 
@@ -136,6 +136,15 @@ int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t 
  * giving each a subset of the levels.  level_ids == NULL selects every level. */
 int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
                            int32_t device_tables, const int32_t* level_ids, int32_t n_level_ids, wbg_plan** out);
+/* Same, restricted to ROW BANDS of levels: `bands` holds n_bands triples (level, first window-tile row, number of
+ * window-tile rows), ascending and unique in `level`; a window-tile row is `tile_rows` window rows as reported by
+ * wbg_cascade_tile for the model's window.  Only the windows of the band are scanned (model.py:243 restricted to those
+ * rows) and only the channel rows they read are computed -- level 0 alone is 16 % of a pyramid, so whole levels cap
+ * an 8-GPU split of one frame at about 6x; bands make the split even.  Levels not listed are not computed. */
+int wbg_plan_create_bands(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
+                          int32_t device_tables, const int32_t* bands, int32_t n_bands, wbg_plan** out);
+/* window tile of the cascade kernel for a win_m x win_n x channels model: tile_rows x tile_cols windows per CTA */
+int wbg_cascade_tile(int32_t win_m, int32_t win_n, int32_t channels, int32_t* tile_rows, int32_t* tile_cols);
 void wbg_plan_destroy(wbg_plan* plan);
 int wbg_plan_get_info(const wbg_plan* plan, wbg_plan_info* info);
 int wbg_plan_get_levels(const wbg_plan* plan, wbg_level* levels, int32_t cap);

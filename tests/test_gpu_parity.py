@@ -418,6 +418,41 @@ def _hit_diff(got_boxes, got_scores, ref_boxes, ref_scores):
     return missing, extra, moved
 
 
+def test_row_bands_equal_filtered_full_detect():
+    """row-band sharding of one frame (config C on 8 GPUs): the bands of a partition reproduce the full detect -- hits,
+    order after normalisation, and the n_loc / n_weak counters -- for 2, 3 and 8 ranks."""
+    from waldboost_b200 import sharding
+    from waldboost_b200.engine import cascade_tile, plan_geometry
+    frame = S.synthetic_frame(1001, 420, 560)
+    M = make_model((12, 12, 4), OPTS_A, 32, 2, frame, keep_total=2e-2)
+    M.reset()
+    _, full = M.detect_batch(frame[None], return_hits=True)
+    full_stats = (M.n_loc, M.n_weak)
+    plan = plan_geometry(420, 560, OPTS_A, M._spec(), 12, 12)
+    TR, TC = cascade_tile(12, 12, 4)
+    rows = [(lv.win_rows + TR - 1) // TR if lv.win_rows > 0 and lv.win_cols > 0 else 0 for lv in plan.levels]
+    cost = [TR * lv.v for lv in plan.levels]
+    assert full.size > 0
+    for world in (2, 3, 8):
+        parts = sharding.assign_bands(rows, cost, world)
+        loads = [sum(n * cost[l] for l, _, n in p) for p in parts]
+        assert max(loads) - min(loads) <= 2 * max(cost)                  # even to within a tile row of the largest level
+        got, n_loc, n_weak = [], 0, 0
+        for bands in parts:
+            if not bands:
+                continue
+            M.reset()
+            _, h = M.detect_batch(frame[None], return_hits=True, bands=bands)
+            # every hit lies inside one of the rank's bands
+            for l, r0, n in bands:
+                hl = h[h["level"] == l]
+                assert np.all((hl["r"] >= r0 * TR) & (hl["r"] < (r0 + n) * TR))
+            assert set(h["level"].tolist()) <= {l for l, _, _ in bands}
+            got.append(h); n_loc += M.n_loc; n_weak += M.n_weak
+        assert np.array_equal(sharding.normalise_hits(np.concatenate(got)), full)
+        assert (n_loc, n_weak) == full_stats
+
+
 def test_config_C_shape_mag_hist_20x20x10():
     """config C's model shape (20x20 window, 10 channels = grad_mag + 9-bin grad_hist) end to end vs the oracle: the
     hit list is the oracle's, bit for bit (grad_mag's float32 sqrt / division chain included)."""

@@ -12,7 +12,7 @@ WBG_OK, WBG_EINVAL, WBG_ECAP, WBG_ECUDA, WBG_ENOMEM = 0, -1, -2, -3, -4
 WBG_U8, WBG_F32 = 0, 1
 WBG_CH_GRAD_HIST, WBG_CH_GRAD_MAG, WBG_CH_GRAD_MAG_HIST, WBG_CH_FPGA_HIST4_U1, WBG_CH_FPGA_MAG_U1 = 0, 1, 2, 3, 4
 WBG_MAX_BINS, WBG_MAX_NORM, WBG_MAX_CHANNELS = 16, 8, 17
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ChannelOpts(C.Structure):
@@ -55,6 +55,8 @@ SYMBOLS = {
     "wbg_device_count": (C.c_int, []),
     "wbg_plan_create": (C.c_int, [_I32, _I32, C.POINTER(ChannelOpts), _I32, _I32, _I32, C.POINTER(_P)]),
     "wbg_plan_create_levels": (C.c_int, [_I32, _I32, C.POINTER(ChannelOpts), _I32, _I32, _I32, C.POINTER(_I32), _I32, C.POINTER(_P)]),
+    "wbg_plan_create_bands": (C.c_int, [_I32, _I32, C.POINTER(ChannelOpts), _I32, _I32, _I32, C.POINTER(_I32), _I32, C.POINTER(_P)]),
+    "wbg_cascade_tile": (C.c_int, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "wbg_plan_destroy": (None, [_P]),
     "wbg_plan_get_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "wbg_plan_get_levels": (C.c_int, [_P, C.POINTER(Level), _I32]),

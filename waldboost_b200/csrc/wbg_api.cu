@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -145,13 +146,41 @@ extern "C" int wbg_plan_create(int32_t H, int32_t W, const wbg_channel_opts* opt
     return wbg_plan_create_levels(H, W, opts, win_m, win_n, device_tables, nullptr, 0, out);
 }
 
+extern "C" int wbg_cascade_tile(int32_t win_m, int32_t win_n, int32_t channels, int32_t* tile_rows, int32_t* tile_cols) {
+    WBG_REQUIRE(tile_rows && tile_cols, "wbg_cascade_tile: null argument");
+    CascadeGeom g;
+    WBG_REQUIRE(wbg_choose_cascade_geom(win_m, win_n, channels, &g), "wbg_cascade_tile: window %dx%dx%d does not fit the shared-memory tile", win_m, win_n, channels);
+    *tile_rows = g.TR; *tile_cols = g.TC;
+    return WBG_OK;
+}
+
+static int plan_create_impl(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n, int32_t device_tables,
+                            const int32_t* level_ids, int32_t n_level_ids, const int32_t* bands, int32_t n_bands, wbg_plan** out);
+
 extern "C" int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
                                       int32_t device_tables, const int32_t* level_ids, int32_t n_level_ids, wbg_plan** out) {
+    return plan_create_impl(H, W, opts, win_m, win_n, device_tables, level_ids, n_level_ids, nullptr, 0, out);
+}
+
+extern "C" int wbg_plan_create_bands(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n,
+                                     int32_t device_tables, const int32_t* bands, int32_t n_bands, wbg_plan** out) {
+    WBG_REQUIRE(bands && n_bands >= 1, "wbg_plan_create_bands: null band list");
+    return plan_create_impl(H, W, opts, win_m, win_n, device_tables, nullptr, 0, bands, n_bands, out);
+}
+
+// bands: triples (level, first window-tile row, number of window-tile rows), ascending and unique in `level`
+static int plan_create_impl(int32_t H, int32_t W, const wbg_channel_opts* opts, int32_t win_m, int32_t win_n, int32_t device_tables,
+                            const int32_t* level_ids, int32_t n_level_ids, const int32_t* bands, int32_t n_bands, wbg_plan** out) {
     WBG_REQUIRE(out && opts, "wbg_plan_create: null argument");
     *out = nullptr;
     WBG_REQUIRE(n_level_ids >= 0 && (level_ids || n_level_ids == 0), "wbg_plan_create_levels: bad level list");
     for (int i = 1; i < n_level_ids; ++i)
         WBG_REQUIRE(level_ids[i] > level_ids[i - 1], "wbg_plan_create_levels: level ids must be ascending and unique");
+    for (int i = 0; i < n_bands; ++i) {
+        WBG_REQUIRE(i == 0 || bands[3 * i] > bands[3 * (i - 1)], "wbg_plan_create_bands: levels must be ascending and unique");
+        WBG_REQUIRE(bands[3 * i + 1] >= 0 && bands[3 * i + 2] >= 1, "wbg_plan_create_bands: bad band (%d, %d) of level %d", bands[3 * i + 1], bands[3 * i + 2], bands[3 * i]);
+    }
+    WBG_REQUIRE(n_bands == 0 || (win_m > 0 && win_n > 0), "wbg_plan_create_bands: a band plan needs a detector window");
     WBG_REQUIRE(H >= 1 && W >= 1, "wbg_plan_create: bad image size %dx%d", H, W);
     WBG_REQUIRE(opts->shrink == 1 || opts->shrink == 2, "Shrink factor must be integer 1 <= shrink <= 2");
     WBG_REQUIRE(opts->n_per_oct >= 1 && opts->n_per_oct <= 64, "wbg_plan_create: bad n_per_oct %d", opts->n_per_oct);
@@ -214,15 +243,22 @@ extern "C" int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_op
             const long long nwin = (long long)L.win_rows * L.win_cols;
             chn += (long long)wbg_align_up((size_t)L.u * L.v * p->C, 4);
             win += (long long)wbg_align_up((size_t)nwin, 32);
-            // a level outside the requested subset keeps its place in the layout but gets no tiles
+            // a level outside the requested subset keeps its place in the layout but gets no tiles; a row band keeps the
+            // window-tile rows [band_ty0, band_ty0 + band_cnt) of the level
             bool selected = true;
+            int band_ty0 = 0, band_cnt = 1 << 30;
             if (level_ids) {
                 const int id = (int)p->levels.size();
                 while (next_id < n_level_ids && level_ids[next_id] < id) ++next_id;
                 selected = next_id < n_level_ids && level_ids[next_id] == id;
             }
+            if (bands) {
+                const int id = (int)p->levels.size();
+                while (next_id < n_bands && bands[3 * next_id] < id) ++next_id;
+                selected = next_id < n_bands && bands[3 * next_id] == id;
+                if (selected) { band_ty0 = bands[3 * next_id + 1]; band_cnt = bands[3 * next_id + 2]; }
+            }
             L.skipped = selected ? 0 : 1;
-            if (selected) nloc += nwin;
 
             LevelDev D;
             memset(&D, 0, sizeof(D));
@@ -230,17 +266,33 @@ extern "C" int wbg_plan_create_levels(int32_t H, int32_t W, const wbg_channel_op
             D.identity = (nh == h && nw == w) ? 1 : 0;
             D.src_off = p->octaves[k].off; D.chn_off = L.chn_off; D.win_off = L.win_off;
             D.win_rows = L.win_rows; D.win_cols = L.win_cols;
+            // the band in window rows and the channel rows its windows read
+            int wr0 = 0, wr1 = L.win_rows, cr0 = 0, cr1 = L.u;
+            if (bands && selected) {
+                WBG_REQUIRE(p->geom_ok, "wbg_plan_create_bands: window %dx%dx%d does not fit the shared-memory tile", win_m, win_n, p->C);
+                const int all_ty = (L.win_rows + p->geom.TR - 1) / p->geom.TR;
+                if (band_ty0 >= all_ty) { selected = false; L.skipped = 1; }
+                else {
+                    wr0 = band_ty0 * p->geom.TR;
+                    wr1 = (int)std::min<long long>((long long)L.win_rows, (long long)(band_ty0 + std::min(band_cnt, all_ty)) * p->geom.TR);
+                    cr0 = wr0; cr1 = std::min(L.u, wr1 + win_m - 1);
+                }
+            }
+            if (selected) nloc += (long long)(wr1 - wr0) * L.win_cols;
             D.ptile0 = ptile;
             D.ptiles_x = (L.v + PYR_TV - 1) / PYR_TV;
-            D.ptiles_y = selected ? (L.u + PYR_TU - 1) / PYR_TU : 0;
+            D.p_ty0 = cr0 / PYR_TU;
+            D.ptiles_y = selected ? (cr1 + PYR_TU - 1) / PYR_TU - D.p_ty0 : 0;
             ptile += D.ptiles_x * D.ptiles_y;
             D.qtile0 = qtile;
             D.qtiles_x = (L.v + PYR_QTV - 1) / PYR_QTV;
-            qtile += selected ? D.qtiles_x * ((L.u + PYR_QTU - 1) / PYR_QTU) : 0;
+            D.q_ty0 = cr0 / PYR_QTU;
+            qtile += selected ? D.qtiles_x * ((cr1 + PYR_QTU - 1) / PYR_QTU - D.q_ty0) : 0;
             D.ctile0 = ctile;
+            D.c_ty0 = wr0 / (p->geom_ok ? p->geom.TR : 1);
             if (p->geom_ok && nwin > 0 && selected) {
                 D.ctiles_x = (L.win_cols + p->geom.TC - 1) / p->geom.TC;
-                D.ctiles_y = (L.win_rows + p->geom.TR - 1) / p->geom.TR;
+                D.ctiles_y = (wr1 - wr0 + p->geom.TR - 1) / p->geom.TR;
                 ctile += D.ctiles_x * D.ctiles_y;
             }
             D.inv_scale = (float)(1.0 / L.scale);

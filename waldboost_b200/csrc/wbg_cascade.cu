@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
     const int v = L->v, win_rows = L->win_rows, win_cols = L->win_cols, ctiles_x = L->ctiles_x;
     const long long chn_off = L->chn_off, win_off = L->win_off;
     const int local = tile_id - L->ctile0;
-    const int ty = local / ctiles_x, tx = local - ty * ctiles_x;
+    const int ty_ = local / ctiles_x, tx = local - ty_ * ctiles_x, ty = ty_ + L->c_ty0;      // c_ty0: the plan's row band
     const int r0 = ty * p.TR, c0 = tx * p.TC;
     const int rows_valid = min(p.TR, win_rows - r0), cols_valid = min(p.TC, win_cols - c0);
     const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;

@@ -61,8 +61,10 @@ struct LevelDev {
     int qtile0, qtiles_x;             // 16 x 29 tiles of the 4-bin uint8 channel kernel
     int ctile0, ctiles_x, ctiles_y;   // tiles of the cascade kernel
     float inv_scale;                  // float32(1 / scale), model.py:147
-    int pad_;
+    int c_ty0;                        // first cascade tile row of this plan's row band of the level (0 = whole level)
     double zoom_r, zoom_c;            // src_h / nh, src_w / nw as float64 (scipy zoom, grid_mode=True)
+    int p_ty0, q_ty0;                 // first tile row of the band for the two channel-kernel tilings
+    int pad_[2];
 };
 
 struct OctaveInfo {

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_kernel(const PyrParams p) {
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
     const int local = tile_id - L->ptile0;
-    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ty_ = local / L->ptiles_x, tx = local - ty_ * L->ptiles_x, ty = ty_ + L->p_ty0;     // p_ty0: the plan's row band
     const int ou0 = ty * PYR_TU, ov0 = tx * PYR_TV;
 
     const int S = p.S, C = p.C, G = p.G;
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_hist_kernel(const PyrParams
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
     const int local = tile_id - L->ptile0;
-    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ty_ = local / L->ptiles_x, tx = local - ty_ * L->ptiles_x, ty = ty_ + L->p_ty0;     // p_ty0: the plan's row band
     const int ou0 = ty * TU, ov0 = tx * TV;
     const int C = p.C;
     const int ry0 = S * (ou0 - SM) - 1, rx0 = S * (ov0 - SM) - 1;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
     const int local = tile_id - L->qtile0;
-    const int ty = local / L->qtiles_x, tx = local - ty * L->qtiles_x;
+    const int ty_ = local / L->qtiles_x, tx = local - ty_ * L->qtiles_x, ty = ty_ + L->q_ty0;     // q_ty0: the plan's row band
     const int ou0 = ty * H4_TU, ov0 = tx * H4_TV;
     const int ry0 = 2 * (ou0 - 1) - 1, rx0 = 2 * (ov0 - 1) - 1;
     const uint8_t* __restrict__ src = (L->oct == 0)
@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
     const int local = tile_id - L->ptile0;
-    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ty_ = local / L->ptiles_x, tx = local - ty_ * L->ptiles_x, ty = ty_ + L->p_ty0;     // p_ty0: the plan's row band
     const int ou0 = ty * TU, ov0 = tx * TV;
     const int C = p.C;
     const bool has_hist = p.kind == WBG_CH_GRAD_MAG_HIST;
@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_fpga_kernel(const PyrParams
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
     const int local = tile_id - L->ptile0;
-    const int ty = local / L->ptiles_x, tx = local - ty * L->ptiles_x;
+    const int ty_ = local / L->ptiles_x, tx = local - ty_ * L->ptiles_x, ty = ty_ + L->p_ty0;     // p_ty0: the plan's row band
     const int ou0 = ty * TU, ov0 = tx * TV;
     const int C = p.C;
     const bool hist = p.kind == WBG_CH_FPGA_HIST4_U1;

@@ -66,10 +66,15 @@ def _opts_key(channel_opts, spec, max_levels):
 class Plan:
     """Pyramid geometry for one (H, W, channel options, window) -- wraps a wbg_plan handle."""
 
-    def __init__(self, H, W, copts, win_m, win_n, device_tables=True, level_ids=None):
+    def __init__(self, H, W, copts, win_m, win_n, device_tables=True, level_ids=None, bands=None):
         L = N.lib()
         self.handle = C.c_void_p()
-        if level_ids is None:
+        if bands is not None:
+            flat = [int(x) for b in sorted(bands) for x in b]           # triples (level, first tile row, tile rows)
+            arr = (C.c_int32 * max(len(flat), 1))(*flat)
+            code = L.wbg_plan_create_bands(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, arr, len(flat) // 3,
+                                           C.byref(self.handle))
+        elif level_ids is None:
             code = L.wbg_plan_create(H, W, C.byref(copts), win_m, win_n, 1 if device_tables else 0, C.byref(self.handle))
         else:
             ids = sorted(set(int(x) for x in level_ids))
@@ -99,9 +104,16 @@ class Plan:
             pass
 
 
-def plan_geometry(H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None):
+def plan_geometry(H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None, bands=None):
     """Host-only plan (no GPU needed): level sizes, offsets and window counts."""
-    return Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, device_tables=False, level_ids=level_ids)
+    return Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, device_tables=False, level_ids=level_ids, bands=bands)
+
+
+def cascade_tile(win_m, win_n, channels):
+    """(rows, columns) of the cascade kernel's window tile for a win_m x win_n x channels model (host arithmetic)."""
+    tr, tc = C.c_int32(), C.c_int32()
+    N.check(N.lib().wbg_cascade_tile(int(win_m), int(win_n), int(channels), C.byref(tr), C.byref(tc)))
+    return tr.value, tc.value
 
 
 class ModelHandle:
@@ -194,13 +206,14 @@ class Engine:
             self._pinned[name] = t
         return t
 
-    def plan(self, H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None):
+    def plan(self, H, W, channel_opts, spec, win_m=0, win_n=0, max_levels=0, level_ids=None, bands=None):
         lv_key = None if level_ids is None else tuple(sorted(set(int(x) for x in level_ids)))
-        key = (H, W, win_m, win_n, lv_key) + _opts_key(channel_opts, spec, max_levels)
+        bd_key = None if bands is None else tuple(sorted(tuple(int(x) for x in b) for b in bands))
+        key = (H, W, win_m, win_n, lv_key, bd_key) + _opts_key(channel_opts, spec, max_levels)
         p = self._plans.get(key)
         if p is None:
             with self.torch.cuda.device(self.device):
-                p = Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, level_ids=lv_key)
+                p = Plan(H, W, make_channel_opts(channel_opts, spec, max_levels), win_m, win_n, level_ids=lv_key, bands=bd_key)
             if len(self._plans) > 64:
                 self._plans.clear()
             self._plans[key] = p

@@ -119,10 +119,10 @@ class Model:
     def _spec(self):
         return resolve_channels(self.channel_opts["channels"])
 
-    def _plan(self, eng, H, W, levels=None):
+    def _plan(self, eng, H, W, levels=None, bands=None):
         m, n = int(self.shape[0]), int(self.shape[1])
         assert self.channel_opts["shrink"] in [1, 2], "Shrink factor must be integer 1 <= shrink <= 2"
-        return eng.plan(H, W, self.channel_opts, self._spec(), m, n, level_ids=levels)
+        return eng.plan(H, W, self.channel_opts, self._spec(), m, n, level_ids=levels, bands=bands)
 
     # ------------------------------------------------------------------------------------------- reference API
     def channels(self, image):
@@ -156,12 +156,13 @@ class Model:
         rects = np.concatenate([x1, y1, x1 + n, y1 + m], axis=1).astype(np.float32)
         return Boxes(rects).normalized(scale=1.0 / scale)
 
-    def _run(self, images, keep_channels=False, levels=None):
+    def _run(self, images, keep_channels=False, levels=None, bands=None):
         """Shared device pipeline: frames [B,H,W] -> (hits, level_counts, plan, chns or None); updates stats.
-        `levels`: optional subset of pyramid level indices to compute and scan (level sharding)."""
+        `levels`: optional subset of pyramid level indices to compute and scan; `bands`: optional (level, first
+        window-tile row, tile rows) triples -- the units of work when one frame is spread over GPUs."""
         eng = get_engine()
         B, H, W = images.shape
-        plan = self._plan(eng, H, W, levels)
+        plan = self._plan(eng, H, W, levels, bands)
         handle = self._device_model()
         if plan.n_levels == 0:
             return np.empty(0, dtype=_hit_dtype()), np.zeros((B, 0), np.int32), plan, None
@@ -217,7 +218,7 @@ class Model:
         assert tuple(X.shape[1:]) == tuple(int(v) for v in self.shape), f"Invalid sample shape {X.shape[1:]}, expected {tuple(self.shape)}"
         return get_engine().predict_samples(self._device_model(), X)
 
-    def detect_batch(self, images, return_hits=False, levels=None):
+    def detect_batch(self, images, return_hits=False, levels=None, bands=None):
         """Detect on a batch of equally sized frames (array [B,H,W] or list of 2-D arrays) -> list of Boxes.
         With return_hits=True also returns the raw hit records (frame, level, r, c, score, box)."""
         if not isinstance(images, np.ndarray):
@@ -226,7 +227,7 @@ class Model:
             images = np.stack(images)
         if images.ndim != 3:
             raise ValueError("detect_batch takes [B,H,W] frames")
-        hits, counts, _, _ = self._run(np.ascontiguousarray(images), levels=levels)
+        hits, counts, _, _ = self._run(np.ascontiguousarray(images), levels=levels, bands=bands)
         per_frame = counts.sum(axis=1) if counts.size else np.zeros(images.shape[0], np.int64)
         # one (N,4) box array and one score array for the whole batch; the per-frame Boxes are views into them
         all_boxes = np.stack([hits["x1"], hits["y1"], hits["x2"], hits["y2"]], axis=1) if hits.size else np.empty((0, 4), np.float32)

@@ -29,6 +29,30 @@ def assign_levels(costs, world):
     return [sorted(x) for x in out]
 
 
+def assign_bands(level_tile_rows, level_row_cost, world):
+    """Split one frame's pyramid into `world` contiguous pieces of (nearly) equal cost.
+
+    The work is laid out as one sequence -- the window-tile rows of level 0, then those of level 1, ... -- where a tile
+    row of level l costs level_row_cost[l] (~ its channel pixels), and the sequence is cut into `world` runs.  A rank
+    therefore gets at most ONE contiguous band of any level (what wbg_plan_create_bands takes), and the pieces differ
+    by at most one tile row of the largest level.  Returns, per rank, a list of (level, first tile row, tile rows)."""
+    items = [(l, r, float(level_row_cost[l])) for l, n in enumerate(level_tile_rows) for r in range(int(n))]
+    total = sum(c for *_, c in items)
+    out = [[] for _ in range(world)]
+    if not items:
+        return out
+    acc, k = 0.0, 0
+    for l, r, c in items:
+        # the item goes to the rank whose cost interval contains its midpoint
+        k = min(world - 1, int((acc + 0.5 * c) * world / total)) if total > 0 else 0
+        if out[k] and out[k][-1][0] == l and out[k][-1][1] + out[k][-1][2] == r:
+            out[k][-1] = (l, out[k][-1][1], out[k][-1][2] + 1)
+        else:
+            out[k].append((l, r, 1))
+        acc += c
+    return out
+
+
 def normalise_hits(hits):
     """Order hit records like the reference's output: (frame, level, r, c) ascending (model.py:173-179 per frame)."""
     if hits.size == 0:
@@ -37,12 +61,14 @@ def normalise_hits(hits):
     return hits[order]
 
 
-def gather_hits(local_hits, local_stats, group=None, dst=0):
+def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
     """Host-side gather of per-rank hit records (frame indices already global) and (n_loc, n_weak) counters.
-    Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere."""
+    Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere.
+    `presorted`: every rank's list is already in that order and the ranks hold ascending frame ranges (image
+    sharding), so concatenating in rank order needs no sort."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return normalise_hits(local_hits), tuple(int(x) for x in local_stats)
+        return (local_hits if presorted else normalise_hits(local_hits)), tuple(int(x) for x in local_stats)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     payload = (local_hits.tobytes(), local_hits.dtype.descr, tuple(int(x) for x in local_stats))
@@ -53,7 +79,7 @@ def gather_hits(local_hits, local_stats, group=None, dst=0):
     parts = [np.frombuffer(b, dtype=np.dtype(d)) for b, d, _ in bucket]
     hits = np.concatenate(parts) if parts else local_hits
     stats = (sum(s[0] for *_, s in bucket), sum(s[1] for *_, s in bucket))
-    return normalise_hits(hits), stats
+    return (hits if presorted else normalise_hits(hits)), stats
 
 
 def detect_sharded(detect_fn, frames, group=None, dst=0):
