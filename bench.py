@@ -420,23 +420,33 @@ def run_config_c(args):
     cost = [TR * lv.v for lv in plan.levels]
     mine = sharding.assign_bands(rows, cost, world)[rank]
 
+    t_detect = [0.0]
+
     def step():
         model.reset()
+        ta = time.perf_counter()
         _, h = model.detect_batch(frame, return_hits=True, bands=mine)
+        t_detect[0] += time.perf_counter() - ta
         return sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0)
 
     for _ in range(max(args.warmup, 3)):
         hits, stats = step()
+    t_detect[0] = 0.0
     barrier()
+    eng = get_engine()
+    eng.profile_enable(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         hits, stats = step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    dev_ms = sum(ms for ms, _ in prof.values()) / args.steps        # this rank's two dominant kernels per step
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, dev_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt, dev_ms = float(t[0].item()), float(t[1].item())
     barrier()
     if rank == 0:
         g = np.load(os.path.join(ROOT, "tests", "golden", "configC_detect.npz"))
@@ -452,6 +462,9 @@ def run_config_c(args):
                        "windows": int(plan.info.n_loc), "levels": plan.n_levels, "bands_rank0": len(mine),
                        "parallelism": f"(level, row band) x{world}, host gather of hits, no collective on data",
                        "hits": int(hits.size), "matches_reference_golden": same,
+                       "device_ms_per_step_max_over_ranks": dev_ms,      # level kernel + cascade kernel of the slowest rank (CUDA events)
+                       "rank0_detect_ms_per_step": 1e3 * t_detect[0] / args.steps,
+                       "rank0_gather_and_wait_ms_per_step": 1e3 * (dt - t_detect[0]) / args.steps,
                        "timed_region": "public API per step on every rank: H2D of the 8.3 MB frame, bands of pyramid + cascade, D2H of hits, gloo gather on rank 0"},
             "e2e": {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(frame.nbytes) * world,
                     "d2h_bytes_per_step": int(hits.nbytes)},

@@ -69,16 +69,38 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return (local_hits if presorted else normalise_hits(local_hits)), tuple(int(x) for x in local_stats)
+    import torch
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    payload = (local_hits.tobytes(), local_hits.dtype.descr, tuple(int(x) for x in local_stats))
-    bucket = [None] * world if rank == dst else None
-    dist.gather_object(payload, bucket, dst=dst, group=group)
-    if rank != dst:
-        return None, None
-    parts = [np.frombuffer(b, dtype=np.dtype(d)) for b, d, _ in bucket]
+    backend = dist.get_backend(group)
+    if backend != "gloo":
+        # device-side backends would move the records through GPU memory: use the (slower) object gather there
+        payload = (local_hits.tobytes(), local_hits.dtype.descr, tuple(int(x) for x in local_stats))
+        bucket = [None] * world if rank == dst else None
+        dist.gather_object(payload, bucket, dst=dst, group=group)
+        if rank != dst:
+            return None, None
+        parts = [np.frombuffer(b, dtype=np.dtype(d)) for b, d, _ in bucket]
+        stats = (sum(s[0] for *_, s in bucket), sum(s[1] for *_, s in bucket))
+    else:
+        # host memory, two collectives, no pickling: the counts (and counters) of every rank, then the records padded to
+        # the longest list
+        item = local_hits.dtype.itemsize
+        hdr = torch.tensor([int(local_hits.size), int(local_stats[0]), int(local_stats[1])], dtype=torch.int64)
+        all_hdr = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_hdr, hdr, group=group)
+        counts = [int(h[0]) for h in all_hdr]
+        cap = max(max(counts), 1) * item
+        buf = torch.zeros(cap, dtype=torch.uint8)
+        if local_hits.size:
+            buf[:local_hits.size * item] = torch.from_numpy(np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1))
+        bucket = [torch.empty(cap, dtype=torch.uint8) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, bucket, dst=dst, group=group)
+        if rank != dst:
+            return None, None
+        parts = [b.numpy()[:c * item].view(local_hits.dtype) for b, c in zip(bucket, counts)]
+        stats = (sum(int(h[1]) for h in all_hdr), sum(int(h[2]) for h in all_hdr))
     hits = np.concatenate(parts) if parts else local_hits
-    stats = (sum(s[0] for *_, s in bucket), sum(s[1] for *_, s in bucket))
     return (hits if presorted else normalise_hits(hits)), stats
 
 
