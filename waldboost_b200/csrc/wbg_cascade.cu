@@ -32,6 +32,16 @@
 
 #include "wbg_internal.h"
 
+// -DWBG_CHECKED: device-side bounds assertions on every index the cascade kernel derives from data (pool positions,
+// window offsets inside the patch, window-mask indices).  compute-sanitizer is closed on the GPU pool this was developed
+// on; the checked build run over the GPU test-suite stands in for memcheck (profiles/r02_checked_build.log).
+#ifdef WBG_CHECKED
+#include <assert.h>
+#define WBG_DEV_ASSERT(c) assert(c)
+#else
+#define WBG_DEV_ASSERT(c) ((void)0)
+#endif
+
 __constant__ StageD2 c_d2[D2_MAX_STAGES];
 
 constexpr int WBG_DBG_TILES = 16384;     // tiles covered by the per-tile debug log
@@ -277,6 +287,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 // A window that passed all T stages: its bit in the per-frame window mask and its score in the dense score map
 // (emit_hits ranks the mask afterwards, which yields the reference's output order).
 __device__ __forceinline__ void mark_survivor(const CascadeParams& p, int frame, long long widx, float score) {
+    WBG_DEV_ASSERT(widx >= 0 && widx < p.score_stride && frame >= 0);
     p.score[(long long)frame * p.score_stride + widx] = score;
     atomicOr(p.mask + (long long)frame * p.mask_stride + (widx >> 5), 1u << (unsigned)(widx & 31));
 }
@@ -377,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
                 wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
                 hs[k] = 0.f;
             } else {
+                WBG_DEV_ASSERT(!has || (idx >= 0 && idx < p.list_cap));
                 wa[k] = tile_base + 4u * (has ? (unsigned)pool_wo[idx] : 0u);
                 hs[k] = has ? pool_hs[idx] : 0.f;
             }
@@ -437,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
             for (int k = 0; k < WPT; ++k) {
                 if (alive[k] != 0.f) {
                     const int pos = base + __popc(bal[k] & ((1u << lane) - 1u));
+                    WBG_DEV_ASSERT(pos >= 0 && pos < p.list_cap && ((wa[k] - tile_base) >> 2) < (unsigned)p.plane);
                     pool_wo[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
                     pool_hs[pos] = hs[k];
                 }
