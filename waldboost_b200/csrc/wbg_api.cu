@@ -309,10 +309,21 @@ static int plan_create_impl(int32_t H, int32_t W, const wbg_channel_opts* opts, 
         if (e == cudaSuccess) e = cudaMalloc(&p->d_levels, p->dev_levels.size() * sizeof(LevelDev));
         if (e == cudaSuccess)
             e = cudaMemcpy(p->d_levels, p->dev_levels.data(), p->dev_levels.size() * sizeof(LevelDev), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && p->qtiles > 0 && p->dev_levels.size() < 65535) {
+            // tile -> level table of the 4-bin uint8 channel kernel
+            std::vector<unsigned short> tl((size_t)p->qtiles);
+            for (size_t l = 0; l < p->dev_levels.size(); ++l) {
+                const int t0 = p->dev_levels[l].qtile0, t1 = l + 1 < p->dev_levels.size() ? p->dev_levels[l + 1].qtile0 : p->qtiles;
+                for (int t = t0; t < t1; ++t) tl[(size_t)t] = (unsigned short)l;
+            }
+            e = cudaMalloc(&p->d_qtile_level, tl.size() * sizeof(unsigned short));
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_qtile_level, tl.data(), tl.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) {
             wbg_set_error("wbg_plan_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
             cudaGetLastError();
             if (p->d_levels) cudaFree(p->d_levels);
+            if (p->d_qtile_level) cudaFree(p->d_qtile_level);
             delete p;
             return WBG_ECUDA;
         }
@@ -324,6 +335,7 @@ static int plan_create_impl(int32_t H, int32_t W, const wbg_channel_opts* opts, 
 extern "C" void wbg_plan_destroy(wbg_plan* plan) {
     if (!plan) return;
     if (plan->d_levels) cudaFree(plan->d_levels);
+    if (plan->d_qtile_level) cudaFree(plan->d_qtile_level);
     delete plan;
 }
 

@@ -33,7 +33,10 @@ static inline size_t wbg_align_up(size_t x, size_t a) { return (x + a - 1) / a *
 constexpr int PYR_TU = 16;
 constexpr int PYR_TV = 32;
 constexpr int PYR_THREADS = 256;
-constexpr int PYR_QTU = 16, PYR_QTV = 29;       // tile of level_hist4_u8_kernel
+#ifndef WBG_H4_TU
+#define WBG_H4_TU 16      // measured on B200, ms per 64 x 1080p: 16 rows x 8 warps x 7 CTAs/SM 5.38, 16 x 9 x 6: 5.68, 32 x 8 x 4: 5.77, 32 x 9 x 4: 5.59
+#endif
+constexpr int PYR_QTU = WBG_H4_TU, PYR_QTV = 29;       // tile of level_hist4_u8_kernel
 
 // Tile of the cascade kernel: TR x TC windows, channel patch (TR+m-1) x (TC+n-1) x C staged planar in smem.
 struct CascadeGeom {
@@ -84,6 +87,7 @@ struct wbg_plan {
     bool geom_ok = false;
     int device = -1;
     LevelDev* d_levels = nullptr;  // device copy of dev_levels
+    unsigned short* d_qtile_level = nullptr;   // level of every tile of the 4-bin uint8 channel kernel (one frame)
 };
 
 // Node record of the generic cascade kernel (16 bytes, read with one 128-bit load).

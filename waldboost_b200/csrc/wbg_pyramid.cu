@@ -158,6 +158,7 @@ struct PyrParams {
     int n_oct;
     const LevelDev* levels;
     int n_levels, tiles_per_frame;
+    const unsigned short* qtile_level;   // level of every tile of the 4-bin uint8 kernel (per frame), or null
     float* chns;
     long long chn_stride;
     int C, S, smooth, kind, n_bins, full, G, fast4;
@@ -601,11 +602,22 @@ __global__ void __launch_bounds__(PYR_THREADS) level_hist_kernel(const PyrParams
 //     float32 is exact -- no float64 at all.  The only exception, a smoothed |gy| sum of exactly 0 next to non-zero
 //     gx (the reference then yields ~1e-14 from gx*6.1e-17), is recomputed with the reference's float64 expression;
 //   * bins 1 and 3 keep NumPy's float64 projection and Numba's float64 smoothing.
-constexpr int H4_TU = 16, H4_TV = 29, H4_WARPS = 9, H4_THREADS = 32 * H4_WARPS;
+#ifndef WBG_H4_WARPS
+#define WBG_H4_WARPS 8
+#endif
+constexpr int H4_TU = PYR_QTU, H4_TV = 29, H4_WARPS = WBG_H4_WARPS, H4_THREADS = 32 * H4_WARPS;
 constexpr int H4_PH = H4_TU + 2, H4_PW = H4_TV + 2, H4_RH = 2 * H4_PH + 2, H4_RW = 2 * H4_PW + 2;   // 18, 31, 38, 64
 static_assert(H4_RW == 64, "a resized tile row must be two warp-wide chunks");
+static_assert(H4_TU == PYR_QTU && H4_TV == PYR_QTV, "the plan counts the tiles of this kernel with PYR_QTU x PYR_QTV");
 
 __device__ __forceinline__ float u8_to_f32(unsigned q) { return __int_as_float(0x4B000000u | q) - 8388608.f; }
+
+// cos(pi/4) of the reference's orientation table (np.cos(np.linspace(0, pi, 5)[1]) = 0x1.6a09e667f3bcdp-1) as two float32:
+// for the integer gradients of a uint8 image, fma(d, C_HI, d * C_LO) with d = gx - gy (bin 1) or gx + gy (bin 3) equals
+// the reference's float32(float64(gx) * cos - float64(gy) * sin) for ALL 2041^2 pairs except d == 0 with gx != 0, where the
+// reference yields the O(1e-13) difference of two float64 roundings instead of 0 (cos(pi/4) and sin(pi/4) differ in the
+// last bit) -- exhaustive check: profiles/prove_hist4_fp32_bins.py.  Those pixels take the float64 expression.
+constexpr float H4_C_HI = 0x1.6a09e6p-1f, H4_C_LO = 0x1.9fcef4p-27f;
 
 // reference arithmetic for one smoothed bin-2 value (rare path, see above): channels.py:50, :61-64, :78-83
 __device__ __noinline__ float hist4_exact_bin2(const float* __restrict__ s_R, int oy, int ox, double c2, double s2) {
@@ -637,7 +649,7 @@ __device__ __noinline__ float hist4_exact_bin2(const float* __restrict__ s_R, in
 }
 
 #ifndef H4_MINB
-#define H4_MINB 6
+#define H4_MINB (WBG_H4_TU == 16 ? 7 : 4)
 #endif
 __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(const PyrParams p) {
     constexpr int PH = H4_PH, PW = H4_PW, RH = H4_RH, RW = H4_RW;
@@ -650,10 +662,16 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x / p.tiles_per_frame;
     const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
-    int lo = 0, hi = p.n_levels - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (p.levels[mid].qtile0 <= tile_id) lo = mid; else hi = mid - 1;
+    int lo;
+    if (p.qtile_level) {
+        lo = (int)__ldg(p.qtile_level + tile_id);           // one load instead of a dependent chain of ~6
+    } else {
+        lo = 0;
+        int hi = p.n_levels - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.levels[mid].qtile0 <= tile_id) lo = mid; else hi = mid - 1;
+        }
     }
     const LevelDev* __restrict__ L = p.levels + lo;
     const int nh = L->nh, nw = L->nw, u = L->u, v = L->v, sh = L->src_h, sw = L->src_w;
@@ -682,43 +700,45 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
 #define H4_P1_UNROLL 2
 #endif
     constexpr int kP1Unroll = H4_P1_UNROLL;
-    // the column taps of a lane's two columns stay in registers for the whole phase
-    const int c0i0 = s_tapc[lane].i0, c0i1 = s_tapc[lane].i1, c1i0 = s_tapc[32 + lane].i0, c1i1 = s_tapc[32 + lane].i1;
-    const float c0w = s_tapc[lane].w1f, c1w = s_tapc[32 + lane].w1f;
+    {
+        // the column taps of a lane's two columns stay in registers for the whole phase
+        const int c0i0 = s_tapc[lane].i0, c0i1 = s_tapc[lane].i1, c1i0 = s_tapc[32 + lane].i0, c1i1 = s_tapc[32 + lane].i1;
+        const float c0w = s_tapc[lane].w1f, c1w = s_tapc[32 + lane].w1f;
 #pragma unroll kP1Unroll
-    for (int task = warp; task < 2 * RH; task += H4_WARPS) {
-        const int iy = task >> 1, ix = ((task & 1) << 5) + lane;
-        const TapF* a = s_tapr + iy;
-        const TapF* b = s_tapc + ix;
-        const uint8_t* __restrict__ r0p = src + (long long)a->i0 * sw;
-        const uint8_t* __restrict__ r1p = src + (long long)a->i1 * sw;
-        const int bi0 = (task & 1) ? c1i0 : c0i0, bi1 = (task & 1) ? c1i1 : c0i1;
-        float val;
-        if (identity) {
-            val = u8_to_f32(__ldg(r0p + bi0));
-        } else {
-            const unsigned q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
-            const float f00 = u8_to_f32(q00), f01 = u8_to_f32(q01), f10 = u8_to_f32(q10), f11 = u8_to_f32(q11);
-            const float wx = (task & 1) ? c1w : c0w, wy = a->w1f;
-            const float top = fmaf(wx, f01 - f00, f00), bot = fmaf(wx, f11 - f10, f10);
-            const float r = fmaf(wy, bot - top, top);
-            val = __fadd_rd(r, 12582912.f) - 12582912.f;            // floor(r) for |r| < 2^22
-            const float fr = r - val;
-            // the float32 estimate is within 1e-4 of scipy's float64 sum: away from an integer both truncate alike
-            if (fabsf(fr - 0.5f) > 0.5f - RESAMPLE_DELTA) {
-                if ((q00 | q01 | q10 | q11) == 0u) {
-                    val = 0.f;
-                } else {
-                    const double w0r = a->w0, w1r = a->w1, w0c = b->w0, w1c = b->w1;
-                    double t = __dmul_rn(__dmul_rn((double)q00, w0r), w0c);
-                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, w0r), w1c));
-                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, w1r), w0c));
-                    t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, w1r), w1c));
-                    val = finish_resample<uint8_t>(t, mm.x, mm.y);
+        for (int task = warp; task < 2 * RH; task += H4_WARPS) {
+            const int iy = task >> 1, ix = ((task & 1) << 5) + lane;
+            const TapF* a = s_tapr + iy;
+            const uint8_t* __restrict__ r0p = src + (long long)a->i0 * sw;
+            const uint8_t* __restrict__ r1p = src + (long long)a->i1 * sw;
+            const int bi0 = (task & 1) ? c1i0 : c0i0, bi1 = (task & 1) ? c1i1 : c0i1;
+            float val;
+            if (identity) {
+                val = u8_to_f32(__ldg(r0p + bi0));
+            } else {
+                const unsigned q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
+                const float f00 = u8_to_f32(q00), f01 = u8_to_f32(q01), f10 = u8_to_f32(q10), f11 = u8_to_f32(q11);
+                const float wx = (task & 1) ? c1w : c0w, wy = a->w1f;
+                const float top = fmaf(wx, f01 - f00, f00), bot = fmaf(wx, f11 - f10, f10);
+                const float r = fmaf(wy, bot - top, top);
+                val = __fadd_rd(r, 12582912.f) - 12582912.f;            // floor(r) for |r| < 2^22
+                const float fr = r - val;
+                // the float32 estimate is within 1e-4 of scipy's float64 sum: away from an integer both truncate alike
+                if (fabsf(fr - 0.5f) > 0.5f - RESAMPLE_DELTA) {
+                    if ((q00 | q01 | q10 | q11) == 0u) {
+                        val = 0.f;
+                    } else {
+                        const TapF* b = s_tapc + ix;
+                        const double w0r = a->w0, w1r = a->w1, w0c = b->w0, w1c = b->w1;
+                        double t = __dmul_rn(__dmul_rn((double)q00, w0r), w0c);
+                        t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q01, w0r), w1c));
+                        t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q10, w1r), w0c));
+                        t = __dadd_rn(t, __dmul_rn(__dmul_rn((double)q11, w1r), w1c));
+                        val = finish_resample<uint8_t>(t, mm.x, mm.y);
+                    }
                 }
             }
+            s_R[iy * RW + ix] = val;
         }
-        s_R[iy * RW + ix] = val;
     }
     __syncthreads();
 
@@ -758,15 +778,28 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
         const float a0 = ((fabsf(gx[0][0]) + fabsf(gx[1][0])) + fabsf(gx[0][1])) + fabsf(gx[1][1]);
         const float a2 = ((fabsf(gy[0][0]) + fabsf(gy[1][0])) + fabsf(gy[0][1])) + fabsf(gy[1][1]);
         float ch1[2][2], ch3[2][2];
+        bool degenerate = false;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                const double gxd = (double)gx[a][b], gyd = (double)gy[a][b];
-                // channels.py:50 under NumPy 2: float64 products and difference, one rounding to float32
-                ch1[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c1), -__dmul_rn(gyd, s1)));
-                ch3[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c3), -__dmul_rn(gyd, s3)));
+                // channels.py:50 without float64: two-float32 product of the integer d with cos(pi/4) (see H4_C_HI)
+                const float d1 = gx[a][b] - gy[a][b], d3 = gx[a][b] + gy[a][b];
+                ch1[a][b] = fabsf(fmaf(d1, H4_C_HI, d1 * H4_C_LO));
+                ch3[a][b] = fabsf(fmaf(d3, H4_C_HI, d3 * H4_C_LO));
+                degenerate |= (d1 == 0.f || d3 == 0.f) && gx[a][b] != 0.f;
             }
+        if (degenerate) {
+            // gx == +-gy != 0: the reference's float64 products do not cancel exactly
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double gxd = (double)gx[a][b], gyd = (double)gy[a][b];
+                    ch1[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c1), -__dmul_rn(gyd, s1)));
+                    ch3[a][b] = fabsf((float)__dadd_rn(__dmul_rn(gxd, c3), -__dmul_rn(gyd, s3)));
+                }
+        }
         const float a1 = __fadd_rn(__fadd_rn(__fadd_rn(ch1[0][0], ch1[1][0]), ch1[0][1]), ch1[1][1]);
         const float a3 = __fadd_rn(__fadd_rn(__fadd_rn(ch3[0][0], ch3[1][0]), ch3[0][1]), ch3[1][1]);
         s_P02[py * PW + px] = make_float2(a0 * 0.25f, a2 * 0.25f);
@@ -1311,10 +1344,15 @@ static int launch_pyramid_t(const wbg_plan* plan, const T* img, int batch, float
         // the orientation table of the default 4-bin histogram: cos/sin = (1,0), (c,s), (6.1e-17,1), (-s,c)
         p.fast4 = (o.n_bins == 4 && !o.full && o.cos_t[0] == 1.0 && o.sin_t[0] == 0.0 && o.sin_t[2] == 1.0 &&
                    o.cos_t[2] > -1e-15 && o.cos_t[2] < 1e-15) ? 1 : 0;
-        if (sizeof(T) == 1 && p.fast4 && o.bias == 0.f && o.shrink == 2 && o.smooth == 1 && !getenv("WBG_PYR_GENERIC")) {
+        // the 4-bin uint8 kernel replaces the float64 projection on bins 1 and 3 by a float32 expression that was checked
+        // against exactly these table entries (profiles/prove_hist4_fp32_bins.py)
+        const bool pi4 = o.cos_t[1] == 0x1.6a09e667f3bcdp-1 && o.sin_t[1] == 0x1.6a09e667f3bccp-1 &&
+                         o.cos_t[3] == -0x1.6a09e667f3bccp-1 && o.sin_t[3] == 0x1.6a09e667f3bcdp-1;
+        if (sizeof(T) == 1 && p.fast4 && pi4 && o.bias == 0.f && o.shrink == 2 && o.smooth == 1 && !getenv("WBG_PYR_GENERIC")) {
             const long long grid_q = (long long)plan->qtiles * batch;
             WBG_REQUIRE(grid_q <= 0x7fffffffLL, "channel pyramid: too many tiles (%lld)", grid_q);
             p.tiles_per_frame = plan->qtiles;
+            p.qtile_level = plan->d_qtile_level;
             WBG_CUDA_TRY(cudaFuncSetAttribute(level_hist4_u8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);
             level_hist4_u8_kernel<<<(unsigned)grid_q, H4_THREADS, 0, stream>>>(p);
