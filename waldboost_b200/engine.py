@@ -338,8 +338,21 @@ class Engine:
             hit_cap = self.default_hit_cap(plan, B)
         while True:
             hits_t, meta, nbytes = self.cascade_launch(model_handle, plan, chns, B, hit_cap)
-            n_hits, stats, counts = self._read_meta(meta, nbytes, B, plan.n_levels)
+            # the counters and an optimistic prefix of the hit list come back with ONE synchronisation (the list is short
+            # in practice); a longer list costs a second copy
+            pre = min(hit_cap, 2048) * N.HIT_DTYPE.itemsize
+            host = self.pinned("meta+hits", nbytes + pre)
+            host[:nbytes].copy_(meta[:nbytes], non_blocking=True)
+            host[nbytes:nbytes + pre].copy_(hits_t[:pre], non_blocking=True)
+            self.torch.cuda.current_stream(self.device).synchronize()
+            raw = host.numpy()
+            n_hits = int(raw[:8].view(np.int64)[0])
+            stats = raw[8:8 + 16 * B].view(np.uint64).reshape(B, 2).copy()
+            counts = raw[8 + 16 * B:nbytes].view(np.int32).reshape(B, plan.n_levels).copy()
             if n_hits <= hit_cap:
+                nb = n_hits * N.HIT_DTYPE.itemsize
+                if nb <= pre:
+                    return raw[nbytes:nbytes + nb].view(N.HIT_DTYPE).copy(), counts, stats
                 return self._read_hits(hits_t, n_hits), counts, stats
             hit_cap = n_hits  # WBG_ECAP semantics: only the first hit_cap were stored -> re-run with room for all
 
