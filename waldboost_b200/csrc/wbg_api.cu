@@ -319,11 +319,22 @@ static int plan_create_impl(int32_t H, int32_t W, const wbg_channel_opts* opts, 
             e = cudaMalloc(&p->d_qtile_level, tl.size() * sizeof(unsigned short));
             if (e == cudaSuccess) e = cudaMemcpy(p->d_qtile_level, tl.data(), tl.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
         }
+        if (e == cudaSuccess && p->ctiles > 0 && p->dev_levels.size() < 65535) {
+            // tile -> level table of the cascade kernel
+            std::vector<unsigned short> tl((size_t)p->ctiles);
+            for (size_t l = 0; l < p->dev_levels.size(); ++l) {
+                const int t0 = p->dev_levels[l].ctile0, t1 = l + 1 < p->dev_levels.size() ? p->dev_levels[l + 1].ctile0 : p->ctiles;
+                for (int t = t0; t < t1; ++t) tl[(size_t)t] = (unsigned short)l;
+            }
+            e = cudaMalloc(&p->d_ctile_level, tl.size() * sizeof(unsigned short));
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_ctile_level, tl.data(), tl.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) {
             wbg_set_error("wbg_plan_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
             cudaGetLastError();
             if (p->d_levels) cudaFree(p->d_levels);
             if (p->d_qtile_level) cudaFree(p->d_qtile_level);
+            if (p->d_ctile_level) cudaFree(p->d_ctile_level);
             delete p;
             return WBG_ECUDA;
         }
@@ -336,6 +347,7 @@ extern "C" void wbg_plan_destroy(wbg_plan* plan) {
     if (!plan) return;
     if (plan->d_levels) cudaFree(plan->d_levels);
     if (plan->d_qtile_level) cudaFree(plan->d_qtile_level);
+    if (plan->d_ctile_level) cudaFree(plan->d_ctile_level);
     delete plan;
 }
 
@@ -561,7 +573,7 @@ extern "C" int wbg_cascade_scan(const wbg_model* model, const wbg_plan* plan, co
                 plan->win_m, plan->win_n, model->m, model->n);
     WBG_REQUIRE(workspace_bytes >= wbg_cascade_workspace_bytes(plan, batch), "wbg_cascade_scan: workspace too small");
     nvtxRangePushA("wbg_cascade_scan");
-    rc = wbg_launch_cascade(model, plan->d_levels, (int)plan->levels.size(), plan->ctiles, plan->chn_floats, plan->windows,
+    rc = wbg_launch_cascade(model, plan->d_levels, plan->d_ctile_level, (int)plan->levels.size(), plan->ctiles, plan->chn_floats, plan->windows,
                             chns, batch, hits, hit_cap, level_counts, (unsigned long long*)stats, (long long*)n_hits,
                             workspace, workspace_bytes, (cudaStream_t)stream);
     nvtxRangePop();
@@ -605,7 +617,7 @@ extern "C" int wbg_predict_on_image(const wbg_model* model, const float* X, int3
     wbg_store_level_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_level, D);
     WBG_CUDA_TRY(cudaGetLastError());
     int32_t* level_counts = (int32_t*)((char*)workspace + 192);
-    return wbg_launch_cascade(model, d_level, 1, tiles, (long long)u * v * model->C, windows, X, 1, hits, hit_cap,
+    return wbg_launch_cascade(model, d_level, nullptr, 1, tiles, (long long)u * v * model->C, windows, X, 1, hits, hit_cap,
                               level_counts, (unsigned long long*)stats, (long long*)n_hits, (char*)workspace + 256,
                               workspace_bytes - 256, (cudaStream_t)stream);
 }

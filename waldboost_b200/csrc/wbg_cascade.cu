@@ -50,6 +50,7 @@ struct CascadeParams {
     const float* chns;
     long long chn_stride;
     const LevelDev* levels;
+    const unsigned short* ctile_level;   // level of every tile of one frame (or null: binary search over the levels)
     int n_levels, tiles_per_frame;
     const NodeDev* nodes;
     const StageDK4* dk4;
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler as well
     const int frame = blockIdx.x / p.tiles_per_frame;
     const int tile_id = blockIdx.x - frame * p.tiles_per_frame;
-    const int lvl = find_level_by_ctile(p.levels, p.n_levels, tile_id);
+    // one table load instead of a dependent chain of ~6 global loads
+    const int lvl = p.ctile_level ? (int)__ldg(p.ctile_level + tile_id) : find_level_by_ctile(p.levels, p.n_levels, tile_id);
     const LevelDev* __restrict__ L = p.levels + lvl;
     const int v = L->v, win_rows = L->win_rows, win_cols = L->win_cols, ctiles_x = L->ctiles_x;
     const long long chn_off = L->chn_off, win_off = L->win_off;
@@ -720,7 +722,7 @@ size_t wbg_cascade_ws_bytes(long long windows, int n_levels, int batch) {
     return carve(windows, batch, nullptr).total;
 }
 
-int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_levels, int tiles_per_frame,
+int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const unsigned short* d_ctile_level, int n_levels, int tiles_per_frame,
                        long long chn_stride, long long windows, const float* chns, int batch, wbg_hit* hits,
                        long long hit_cap, int32_t* level_counts, unsigned long long* stats, long long* n_hits,
                        void* ws, size_t ws_bytes, cudaStream_t stream) {
@@ -733,7 +735,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_l
     WBG_CUDA_TRY(cudaMemsetAsync(w.mask, 0, (size_t)w.mask_words_padded * 4, stream));
 
     CascadeParams p;
-    p.chns = chns; p.chn_stride = chn_stride; p.levels = d_levels; p.n_levels = n_levels; p.tiles_per_frame = tiles_per_frame;
+    p.chns = chns; p.chn_stride = chn_stride; p.levels = d_levels; p.ctile_level = d_ctile_level; p.n_levels = n_levels; p.tiles_per_frame = tiles_per_frame;
     p.nodes = model->d_nodes; p.dk4 = model->d_dk4; p.theta = model->d_theta; p.N = model->N; p.T = model->T;
     p.C = model->C; p.m = model->m; p.n = model->n;
     p.TR = model->geom.TR; p.TC = model->geom.TC; p.pitch = model->geom.pitch; p.plane = model->geom.plane;

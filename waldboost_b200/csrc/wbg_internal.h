@@ -88,6 +88,7 @@ struct wbg_plan {
     int device = -1;
     LevelDev* d_levels = nullptr;  // device copy of dev_levels
     unsigned short* d_qtile_level = nullptr;   // level of every tile of the 4-bin uint8 channel kernel (one frame)
+    unsigned short* d_ctile_level = nullptr;   // level of every tile of the cascade kernel (one frame)
 };
 
 // Node record of the generic cascade kernel (16 bytes, read with one 128-bit load).
@@ -144,7 +145,7 @@ void wbg_prof_end(int kind, cudaStream_t stream);
 // ------------------------------------------------------------------------------------------------ launchers
 int wbg_launch_pyramid(const wbg_plan* plan, const void* img, int dtype, int batch, float* chns, void* ws,
                        size_t ws_bytes, cudaStream_t stream);
-int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, int n_levels, int tiles_per_frame,
+int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const unsigned short* d_ctile_level, int n_levels, int tiles_per_frame,
                        long long chn_stride, long long windows, const float* chns, int batch, wbg_hit* hits,
                        long long hit_cap, int32_t* level_counts, unsigned long long* stats, long long* n_hits,
                        void* ws, size_t ws_bytes, cudaStream_t stream);
