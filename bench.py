@@ -327,24 +327,24 @@ def run_gpu(args):
     except Exception:
         pass
 
-    def roof(kind, bytes_per_frame, name):
+    def roof(kind, bytes_per_frame, name, symbol):
         ms, n = prof[kind]
         if n == 0:
             return None
         per_launch_s = ms * 1e-3 / n
         ach = bytes_per_frame * B / per_launch_s / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        return {"kernel": symbol, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": (traffic[name]["bytes_per_frame"] * B) if name in traffic else None,
                 "traffic_source": ("profiles/dram_traffic.json: " + traffic[name].get("source", "") + " -- an ncu --set full capture of a 4-frame launch scaled per frame, NOT measured in this run") if name in traffic else None,
                 "algorithmic_bytes_per_launch": int(bytes_per_frame * B),
                 "ms_per_launch": per_launch_s * 1e3, "peak_source": peak_src,
-                # context from the committed ncu capture (profiles/r01_ncu_full_final.csv), not measured in this run:
+                # context from the committed ncu capture (profiles/r02_ncu_full_final.csv), not measured in this run:
                 # both kernels are bound by instruction issue, not by HBM
                 "ncu": {k: v for k, v in traffic.get(name, {}).items() if k.startswith("ncu_")} or None,
                 "share_of_step": ms / n / (ms_total / args.steps)}
 
-    r_pyr = roof("level_kernel", pyr_b, "level_kernel")
-    r_cas = roof("cascade_kernel", cas_b, "cascade_kernel")
+    r_pyr = roof("level_kernel", pyr_b, "level_kernel", "level_hist4_u8_kernel")
+    r_cas = roof("cascade_kernel", cas_b, "cascade_kernel", "cascade_pool_kernel<MODE_D2,512>")
     dominant = r_cas if (r_cas and r_pyr and r_cas["ms_per_launch"] > r_pyr["ms_per_launch"]) else (r_pyr or r_cas)
 
     # kernels of libwbg per step: minmax_init, [minmax unless fused into the first octave step: uint8 frames with even

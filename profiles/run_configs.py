@@ -72,7 +72,7 @@ def config_C():
             "hits": len(boxes), "eval_cost": M.eval_cost, "windows": int(plan.info.n_loc)}
 
 
-def config_D(n_images=200):
+def config_D(n_images=1000):
     opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=wb.channels.grad_hist)
     frames = S.synthetic_frames(16, 480, 640)
     M = calibrated_model((12, 12, 4), opts, 2048, 4, frames[0], 1e-4)

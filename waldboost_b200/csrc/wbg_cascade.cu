@@ -123,6 +123,7 @@ __device__ __forceinline__ float2 lds_v2(unsigned addr) {
 // pipe.  On sm_100 FSETP / FSEL / SEL all issue to the ALU pipe (one warp instruction per 2 cycles per scheduler); a
 // loop body made only of them is bound by that pipe while the FMA pipe idles.
 __device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.le.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fset_gtu(float a, float b) { float d; asm("set.gtu.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }   // !(a <= b)
 __device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
 enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2 };
@@ -188,7 +189,10 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 #ifndef D2_UNROLL
 #define D2_UNROLL 4
 #endif
-        constexpr int kD2Unroll = D2_UNROLL;
+#ifndef D2_UNROLL_SPARSE
+#define D2_UNROLL_SPARSE D2_UNROLL
+#endif
+        constexpr int kD2Unroll = NK >= D2_DEPENDENT_MIN_NK ? D2_UNROLL : D2_UNROLL_SPARSE;
 #pragma unroll kD2Unroll
         for (int s = t; s < t_end; ++s) {
             // offsets, theta and thresholds are only ever used as uniform operands; the four leaves are selected
@@ -232,8 +236,14 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
                 }
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                    const float pa = (xa[k] <= thr1) ? p2 : p3;
-                    const float pb = (xb[k] <= thr4) ? p5 : p6;
+                    // every leaf stays a uniform operand (a select between them would fetch them with indexed constant
+                    // loads into vector registers, which go through a slow unit): exactly one of the two products is
+                    // the leaf and the other is +-0, so the sum is exact, and a running score is never -0, so the
+                    // sign of a zero leaf is moot
+                    const float ca = fset_le(xa[k], thr1), na = fset_gtu(xa[k], thr1);
+                    const float cb = fset_le(xb[k], thr4), nb = fset_gtu(xb[k], thr4);
+                    const float pa = __fmaf_rn(ca, p2, na * p3);
+                    const float pb = __fmaf_rn(cb, p5, nb * p6);
                     const float m0 = fset_le(x0[k], thr0);
                     // m0 ? pa : pb on the FMA pipe, exact for finite leaves: (-m0*pb + pb) is pb or +0, then + m0*pa
                     const float pr = __fmaf_rn(m0, pa, __fmaf_rn(-m0, pb, pb));
