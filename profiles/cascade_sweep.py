@@ -29,7 +29,7 @@ DEFAULT = [
 ]
 variants = json.load(open(sys.argv[2])) if len(sys.argv) > 2 else DEFAULT
 KNOBS = ["WBG_CAS_KERNEL", "WBG_CAS_PACK", "WBG_CAS_ROUND_FULL", "WBG_CAS_ROUND_MID", "WBG_CAS_ROUND_TAIL",
-         "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2", "WBG_CAS_TILE_SKIP", "WBG_CAS_MODE", "WBG_CAS_CUT", "WBG_CAS_X1", "WBG_CAS_X2"]
+         "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2", "WBG_CAS_ROUND_SOLO", "WBG_CAS_TILE_SKIP", "WBG_CAS_MODE", "WBG_CAS_CUT", "WBG_CAS_X1", "WBG_CAS_X2"]
 
 model = wb.Model.load(os.path.join(ROOT, os.environ.get("SWEEP_MODEL", "tests/golden/configB_model.pb")))
 H, Wd = int(os.environ.get("SWEEP_H", 1080)), int(os.environ.get("SWEEP_W", 1920))

@@ -101,8 +101,6 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
-    int cnum = env_int("WBG_CAS_COMPACT_NUM", 3), cden = env_int("WBG_CAS_COMPACT_DEN", 4);
-    if (cnum < 1 || cden <= cnum) { cnum = 3; cden = 4; }
     int idx = 0;
     for (auto& c : cand) {
         if (idx++ < skip) continue;
@@ -116,11 +114,10 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
         if (bytes <= c.budget && plane < 65536) {
             g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
             g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap;
-            g->compact_num = cnum;
-            g->compact_den = cden;
             g->round_full = env_int("WBG_CAS_ROUND_FULL", 32);
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
+            g->round_solo = env_int("WBG_CAS_ROUND_SOLO", 32);
             g->round_n1 = env_int("WBG_CAS_ROUND_N1", 2 * c.threads);
             g->round_n2 = env_int("WBG_CAS_ROUND_N2", 64);
             g->pack = env_int("WBG_CAS_PACK", 1);

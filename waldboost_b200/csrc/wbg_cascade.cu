@@ -58,7 +58,7 @@ struct CascadeParams {
     int N, T;
     int C, m, n;
     int TR, TC, pitch, plane;
-    int list_cap, compact_num, compact_den, round_full, round_mid, round_tail, pack;
+    int list_cap, round_solo, round_full, round_mid, round_tail, pack;
     int round_n1, round_n2;  // pool kernel: round_full stages while more than round_n1 windows are left, round_mid above round_n2
     unsigned long long* dbg; // debug counters (wbg_cascade_counters_enable), else null
     int rec_off;             // byte offset of the staged stage records inside the dynamic shared memory (MODE_DK4)
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) 
             // at most 32 windows are left: warp 0 finishes the cascade on its own, nobody meets at a barrier any more
             if (warp != 0) break;
             while (t < p.T) {
-                int te = min(p.T, t + p.round_tail);
+                int te = min(p.T, t + p.round_solo);
                 if (MODE == MODE_DK4) {
                     te = min(te, t + DK4_ROUND_MAX);
                     const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t);
@@ -754,7 +754,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
     const long long grid = (long long)tiles_per_frame * batch;
     WBG_REQUIRE(grid <= 0x7fffffffLL, "cascade: too many tiles (%lld)", grid);
     const CascadeGeom& g = model->geom;
-    p.list_cap = g.list_cap; p.compact_num = g.compact_num; p.compact_den = g.compact_den;
+    p.list_cap = g.list_cap; p.round_solo = g.round_solo < 1 ? 1 : g.round_solo;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
     const bool use_dk4_req = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
     p.rec_off = (g.smem_bytes + 15) & ~15;

@@ -46,7 +46,7 @@ struct CascadeGeom {
     int smem_bytes;    // dynamic shared memory of the cascade kernel
     int threads, wpt;  // CTA size and window slots per thread: threads * wpt >= TR * TC
     int list_cap;      // capacity of the survivor pool (windows): threads * wpt
-    int compact_num, compact_den;   // re-pack when alive * den <= slots * num   (num/den <= 1/2)
+    int round_solo;                 // stages between liveness checks of the last warp of a tile (at most 32 windows left)
     int round_full, round_mid, round_tail;   // stages per round while slots > threads / > 64 / else
     int round_n1, round_n2;                  // pool kernel: window counts that separate round_full / round_mid / round_tail
     int pack;                                // slots per thread after a re-pack (0 = keep one slot column per thread)
