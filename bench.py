@@ -275,40 +275,51 @@ def run_gpu(args):
     from waldboost_b200 import sharding
     host_group = dist.new_group(backend="gloo") if world > 1 else None
 
+    gatherer = sharding.HitGatherer(group=host_group, dst=0, presorted=True) if world > 1 else None
+
     def e2e_step(src):
+        """detect on this rank's frames; with several ranks the gather of the step's hit records is handed to the
+        gatherer thread (it overlaps the next step's GPU work) and a future is returned in place of the result"""
         out, h = model.detect_batch(src, return_hits=True)
         if world == 1:
             return h, h
         h["frame"] += rank * B                              # global frame indices (detect_batch returns a fresh array)
-        gathered, stats = sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0, presorted=True)
-        return h, gathered
+        return h, gatherer.submit(h, (model.n_loc, model.n_weak))
 
-    for _ in range(2):
-        e2e_step(frames)
+    def e2e_loop(src, n):
+        pending = None
+        for _ in range(n):
+            h, res = e2e_step(src)
+            if world > 1:
+                if pending is not None:
+                    pending.result()                        # at most one gather in flight behind the GPU
+                pending = res
+        torch.cuda.synchronize()
+        return h, (pending.result()[0] if world > 1 else res)   # every gather has completed when the clock stops
+
+    e2e_loop(frames, 2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        hits, gathered = e2e_step(frames)
-    torch.cuda.synchronize()
+    hits, gathered = e2e_loop(frames, args.steps)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e = {"value": frames_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
            "d2h_bytes_per_step": int(hits.nbytes + 8 + 16 * B + 4 * B * plan.n_levels),
-           "host_gather": None if world == 1 else f"hit records of {world} ranks gathered on rank 0 (gloo, host memory) inside the timed region: "
+           "host_gather": None if world == 1 else f"hit records of {world} ranks gathered on rank 0 (gloo, host memory; the gather of a step overlaps the next step's GPU work, all gathers complete inside the timed region): "
                                                    f"{0 if gathered is None else int(gathered.size)} hits per step"}
     # the same call on ordinary (pageable) NumPy frames: the library stages them through a page-locked buffer
     pageable = np.array(frames)
-    e2e_step(pageable)
+    e2e_loop(pageable, 1)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(max(2, args.steps // 3)):
-        e2e_step(pageable)
-    torch.cuda.synchronize()
+    e2e_loop(pageable, max(2, args.steps // 3))
     e2e_pg_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e["pageable"] = {"value": B * max(2, args.steps // 3) * world / e2e_pg_s, "unit": UNIT,
                        "note": "np.ndarray frames that are not page-locked (staged through a pinned buffer by the library)"}
     del pageable
+    if gatherer is not None:
+        gatherer.close()
 
     # ---- roofline of the two dominant kernels (algorithmic bytes per launch / CUDA-event time per launch)
     peaks, peak_src = {}, "fallback 6650 GB/s (B200_PROFILING.md)"

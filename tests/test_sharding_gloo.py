@@ -148,3 +148,40 @@ def test_level_sharded_detect_world2_gloo(tmp_path):
     ref_hits, ref_stats = fn(list(range(len(costs))))
     assert ref_hits.size > 0 and np.array_equal(got["hits"], sharding.normalise_hits(ref_hits))
     assert tuple(got["stats"]) == tuple(ref_stats)
+
+
+def _pipelined_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        sys.path.insert(0, p)
+    from waldboost_b200._native import HIT_DTYPE
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = sharding.HitGatherer(presorted=True)
+    futs = []
+    for step in range(4):                               # ragged and empty lists, several steps in flight
+        n = (3 * step + 2 * rank) % 5
+        h = np.zeros(n, HIT_DTYPE)
+        h["frame"], h["r"], h["c"], h["score"] = 10 * rank + step, np.arange(n), step, rank + 0.5
+        futs.append(g.submit(h, (100 * step + rank, 7)))
+    res = [f.result() for f in futs]
+    g.close()
+    if rank == 0:
+        np.savez(out_path, **{f"hits{i}": r[0] for i, r in enumerate(res)}, stats=np.array([r[1] for r in res]))
+    else:
+        assert all(r == (None, None) for r in res)
+    dist.destroy_process_group()
+
+
+def test_pipelined_gather_world2_gloo(tmp_path):
+    """HitGatherer: gathers submitted back to back come out per step, in rank order, with the counters summed."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "pipe.npz")
+    mp.spawn(_pipelined_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    for step in range(4):
+        h = got[f"hits{step}"]
+        n0, n1 = (3 * step) % 5, (3 * step + 2) % 5
+        assert h.size == n0 + n1
+        assert np.array_equal(h["frame"], [step] * n0 + [10 + step] * n1) and np.array_equal(h["r"], list(range(n0)) + list(range(n1)))
+        assert tuple(got["stats"][step]) == (200 * step + 1, 14)

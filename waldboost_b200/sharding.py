@@ -104,6 +104,24 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
     return (hits if presorted else normalise_hits(hits)), stats
 
 
+class HitGatherer:
+    """Pipelined host gather: `submit()` hands a rank's hit records to ONE background thread that runs `gather_hits`
+    on them, so the collective of step i overlaps the GPU work of step i+1.  Every rank submits in the same order and
+    the single worker thread keeps that order, which is all the process group needs.  `submit` returns a
+    concurrent.futures.Future whose result is what gather_hits returns."""
+
+    def __init__(self, group=None, dst=0, presorted=False):
+        from concurrent.futures import ThreadPoolExecutor
+        self.group, self.dst, self.presorted = group, dst, presorted
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="wbg-gather")
+
+    def submit(self, local_hits, local_stats):
+        return self._pool.submit(gather_hits, local_hits, tuple(int(x) for x in local_stats), self.group, self.dst, self.presorted)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+
 def detect_sharded(detect_fn, frames, group=None, dst=0):
     """Image-sharded detect over the ranks of `group`.
 
