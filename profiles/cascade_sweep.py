@@ -24,12 +24,12 @@ from waldboost_b200.engine import ModelHandle, Plan, get_engine, make_channel_op
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 DEFAULT = [
-    {"name": "v2", "WBG_CAS_KERNEL": "v2"},
-    {"name": "pool"},
+    {"name": "default"},
+    {"name": "rounds 64/128/128", "WBG_CAS_ROUND_FULL": 64, "WBG_CAS_ROUND_MID": 128},
 ]
 variants = json.load(open(sys.argv[2])) if len(sys.argv) > 2 else DEFAULT
-KNOBS = ["WBG_CAS_KERNEL", "WBG_CAS_PACK", "WBG_CAS_ROUND_FULL", "WBG_CAS_ROUND_MID", "WBG_CAS_ROUND_TAIL",
-         "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2", "WBG_CAS_ROUND_SOLO", "WBG_CAS_TILE_SKIP", "WBG_CAS_MODE", "WBG_CAS_CUT", "WBG_CAS_X1", "WBG_CAS_X2"]
+KNOBS = ["WBG_CAS_PACK", "WBG_CAS_ROUND_FULL", "WBG_CAS_ROUND_MID", "WBG_CAS_ROUND_TAIL", "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2",
+         "WBG_CAS_ROUND_SOLO"]
 
 model = wb.Model.load(os.path.join(ROOT, os.environ.get("SWEEP_MODEL", "tests/golden/configB_model.pb")))
 H, Wd = int(os.environ.get("SWEEP_H", 1080)), int(os.environ.get("SWEEP_W", 1920))
@@ -86,8 +86,7 @@ for var in variants:
            "family_ms_per_frame": e0.elapsed_time(e1) / reps / B, "hits": int(hits.size),
            "eval_cost": n_weak / max(int(stats[:, 0].sum()), 1),
            "exec_per_live": execd / max(n_weak, 1), "exec_by_nk": [c / max(n_weak, 1) for c in cnt[:4]],
-           "rounds_per_tile": cnt[5] / max(cnt[7], 1), "guest_frac": cnt[8] / max(cnt[6], 1), "pool_writes_per_window": cnt[6] / max(int(stats[:, 0].sum()), 1),
-           "kcycles_per_tile": {"stage": cnt[9] / max(cnt[7], 1) / 1e3, "first": cnt[10] / max(cnt[7], 1) / 1e3, "n>1024": cnt[11] / max(cnt[7], 1) / 1e3, "n>512": cnt[12] / max(cnt[7], 1) / 1e3, "n>128": cnt[13] / max(cnt[7], 1) / 1e3, "n>32": cnt[14] / max(cnt[7], 1) / 1e3, "solo": cnt[15] / max(cnt[7], 1) / 1e3},
+           "rounds_per_tile": cnt[5] / max(cnt[7], 1), "pool_writes_per_window": cnt[6] / max(int(stats[:, 0].sum()), 1),
            "knobs": {k: v for k, v in var.items() if k != "name"}}
     print(json.dumps(out), flush=True)
     del mh, plan

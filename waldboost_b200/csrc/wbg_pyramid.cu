@@ -601,7 +601,9 @@ __global__ void __launch_bounds__(PYR_THREADS) level_hist_kernel(const PyrParams
 //   * bins 0 and 2 are |gx| and |gy| (cos/sin = 1, 0 and 6.1e-17, 1): small integers, so pooling and smoothing them in
 //     float32 is exact -- no float64 at all.  The only exception, a smoothed |gy| sum of exactly 0 next to non-zero
 //     gx (the reference then yields ~1e-14 from gx*6.1e-17), is recomputed with the reference's float64 expression;
-//   * bins 1 and 3 keep NumPy's float64 projection and Numba's float64 smoothing.
+//   * bins 1 and 3 (the diagonals) are projected in float32 with a two-term constant that reproduces NumPy's float64
+//     expression rounded to float32 for every integer gradient pair (H4_C_HI / H4_C_LO below; gx == +-gy goes through
+//     float64), and keep Numba's float64 smoothing.
 #ifndef WBG_H4_WARPS
 #define WBG_H4_WARPS 8
 #endif
