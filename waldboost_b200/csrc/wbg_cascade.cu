@@ -283,6 +283,9 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 #ifndef CAS_MINB_512x4
 #define CAS_MINB_512x4 3
 #endif
+#ifndef CAS_MINB_DK4
+#define CAS_MINB_DK4 2              // the staged depth-4 records leave room for two 512-thread CTAs per SM: 64 registers, no spills
+#endif
 // ------------------------------------------------------------------------------------------------ pool kernel
 // Same tile, patch and stage loops as cascade_kernel, different bookkeeping between rounds: after EVERY round the
 // survivors of the CTA are appended to a pool in shared memory (window offset + running score; one shared-memory
@@ -304,7 +307,7 @@ __device__ __forceinline__ void mark_survivor(const CascadeParams& p, int frame,
 }
 
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : CAS_MINB_512x4) cascade_pool_kernel(const CascadeParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 4 : 5) : (MODE == MODE_DK4 ? CAS_MINB_DK4 : CAS_MINB_512x4)) cascade_pool_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int WPT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];

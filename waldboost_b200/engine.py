@@ -363,7 +363,10 @@ class Engine:
         torch = self.torch
         B = int(images.shape[0])
         if chunk is None:
-            chunk = int(os.environ.get("WBG_PIPE_CHUNK", "8"))
+            # about eight 1080p frames' worth of pixels per chunk: long enough grids for small frames (a chunk of eight
+            # 640x480 frames is only ~7 waves of cascade tiles), short enough to overlap the copies of large ones
+            auto = max(1, min(256, round(8 * 1920 * 1080 / max(1, int(images.shape[1]) * int(images.shape[2])))))
+            chunk = int(os.environ.get("WBG_PIPE_CHUNK", auto))
         if B <= chunk:
             dev = self.upload_images(images)
             chns = self.pyramid(dev, plan)
