@@ -28,7 +28,7 @@ DEFAULT = [
     {"name": "rounds 64/128/128", "WBG_CAS_ROUND_FULL": 64, "WBG_CAS_ROUND_MID": 128},
 ]
 variants = json.load(open(sys.argv[2])) if len(sys.argv) > 2 else DEFAULT
-KNOBS = ["WBG_CAS_PACK", "WBG_CAS_ROUND_FULL", "WBG_CAS_ROUND_MID", "WBG_CAS_ROUND_TAIL", "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2",
+KNOBS = ["WBG_CAS_GEOM384", "WBG_CAS_PACK", "WBG_CAS_ROUND_FULL", "WBG_CAS_ROUND_MID", "WBG_CAS_ROUND_TAIL", "WBG_CAS_ROUND_N1", "WBG_CAS_ROUND_N2",
          "WBG_CAS_ROUND_SOLO"]
 
 model = wb.Model.load(os.path.join(ROOT, os.environ.get("SWEEP_MODEL", "tests/golden/configB_model.pb")))

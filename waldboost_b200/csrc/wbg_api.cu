@@ -97,7 +97,7 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
     // A larger tile keeps the lanes of the sparse late stages fuller and halves the halo overhead, but fewer
     // resident CTAs hide less of each tile's barrier and tail latency.
     struct Cand { int TR, TC, threads, wpt, budget; };
-    const Cand cand[] = {{32, 64, 512, 4, 74 * 1024}, {32, 32, 256, 4, 44 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
+    const Cand cand[] = {{env_int("WBG_CAS_GEOM384", 0) ? 48 : 32, env_int("WBG_CAS_GEOM384", 0) ? 32 : 64, env_int("WBG_CAS_GEOM384", 0) ? 384 : 512, 4, 74 * 1024}, {32, 32, 256, 4, 44 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates

@@ -307,7 +307,7 @@ __device__ __forceinline__ void mark_survivor(const CascadeParams& p, int frame,
 }
 
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 4 : 5) : (MODE == MODE_DK4 ? CAS_MINB_DK4 : CAS_MINB_512x4)) cascade_pool_kernel(const CascadeParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 4 : 5) : THREADS == 384 ? (MODE == MODE_DK4 ? 3 : 4) : (MODE == MODE_DK4 ? CAS_MINB_DK4 : CAS_MINB_512x4)) cascade_pool_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int WPT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -809,8 +809,9 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
         else if (use_dk4) WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_DK4, TH>), TH);                          \
         else WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_GENERIC, TH>), TH);                                   \
     } while (0)
-    WBG_REQUIRE(g.wpt == 4 && (g.threads == 512 || g.threads == 256), "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
+    WBG_REQUIRE(g.wpt == 4 && (g.threads == 512 || g.threads == 384 || g.threads == 256), "cascade: unsupported tile geometry %d x %d", g.threads, g.wpt);
     if (g.threads == 512) WBG_CAS_LAUNCH_POOL(512);
+    else if (g.threads == 384) WBG_CAS_LAUNCH_POOL(384);
     else WBG_CAS_LAUNCH_POOL(256);
 #undef WBG_CAS_LAUNCH_POOL
 #undef WBG_CAS_LAUNCH_K
