@@ -541,9 +541,13 @@ def test_sample_mode_predict():
         M.predict(np.zeros((3, 12, 12, 3), np.float32))
 
 
-def test_pipelined_batch_matches_frame_by_frame():
-    """batches larger than one pipeline chunk (16 frames) go through the two-stream H2D/compute pipeline: same hits,
-    same order, same counters as frame-by-frame detect(); also exercises the hit-buffer overflow path of a chunk."""
+@pytest.mark.parametrize("chunk,grow", [(4, 1), (4, 4), (2, 8)])
+def test_pipelined_batch_matches_frame_by_frame(monkeypatch, chunk, grow):
+    """batches larger than one pipeline chunk go through the two-stream H2D/compute pipeline (chunks of growing size):
+    same hits, same order, same counters as frame-by-frame detect(); also exercises the hit-buffer overflow path of a
+    chunk.  The chunk is forced small here: by default it is sized by frame pixels and these frames are tiny."""
+    monkeypatch.setenv("WBG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("WBG_PIPE_GROW", str(grow))
     frames = S.synthetic_frames(21, 96, 128)
     M = make_model((12, 12, 4), OPTS_A, 24, 2, frames[0], keep_total=5e-2, calib_levels=2)
     M.reset()

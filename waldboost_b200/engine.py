@@ -374,9 +374,14 @@ class Engine:
         if not hasattr(self, "_pipe_streams"):
             self._pipe_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         cur = torch.cuda.current_stream(self.device)
-        # a short first chunk gets the kernels going while the rest of the batch is still being copied
-        first = max(1, chunk // 4)
-        spans = [(0, first)] + [(lo, min(lo + chunk, B)) for lo in range(first, B, chunk)]
+        # a short first chunk gets the kernels going while the rest of the batch is still being copied; later chunks
+        # grow (their copies hide behind ever longer kernels), so most of the batch runs in a few long launches
+        grow = int(os.environ.get("WBG_PIPE_GROW", "4"))
+        spans, lo, size = [], 0, max(1, chunk // 4)
+        while lo < B:
+            spans.append((lo, min(lo + size, B)))
+            lo += size
+            size = chunk if size < chunk else min(2 * size, grow * chunk)
         jobs = []
         for i, (lo, hi) in enumerate(spans):
             slot = str(i & 1)
