@@ -93,11 +93,16 @@ static int env_int(const char* name, int dflt) {
 
 bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
     // Tile candidates in order of preference (measured on B200 with the config B cascade, ms per 64 frames:
-    // 32x64 windows / 512 threads / 3 CTAs per SM 24.9, 32x128 / 512 x 8 slots / 2 CTAs 25.6, 16x64 / 256 / 5 CTAs 29.2).
-    // A larger tile keeps the lanes of the sparse late stages fuller and halves the halo overhead, but fewer
-    // resident CTAs hide less of each tile's barrier and tail latency.
+    // 32x64 windows / 512 threads / 3 CTAs per SM 24.9, 32x128 / 512 x 8 slots / 2 CTAs 25.6, 16x64 / 256 / 5 CTAs 29.2;
+    // a 48x32 tile with 384 threads / 4 CTAs is 1 % faster, WBG_CAS_GEOM384=1).  A larger tile keeps the lanes of the
+    // sparse late stages fuller and halves the halo overhead, but fewer resident CTAs hide less of each tile's barrier
+    // and tail latency.  Large windows or many channels (config C: 20x20x10) take the third entry: 32x32 windows with
+    // 512 threads, two CTAs per SM (1.04 ms per 4K frame against 1.53 with the 16x32 / 256-thread tile further down
+    // and 1.22 with one 32x64 CTA per SM).
     struct Cand { int TR, TC, threads, wpt, budget; };
-    const Cand cand[] = {{env_int("WBG_CAS_GEOM384", 0) ? 48 : 32, env_int("WBG_CAS_GEOM384", 0) ? 32 : 64, env_int("WBG_CAS_GEOM384", 0) ? 384 : 512, 4, 74 * 1024}, {32, 32, 256, 4, 44 * 1024}, {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
+    const bool g384 = env_int("WBG_CAS_GEOM384", 0) != 0;
+    const Cand cand[] = {{g384 ? 48 : 32, g384 ? 32 : 64, g384 ? 384 : 512, 4, 74 * 1024}, {32, 32, 256, 4, 44 * 1024}, {32, 32, 512, 4, 112 * 1024},
+                         {16, 64, 256, 4, 100 * 1024}, {16, 32, 256, 4, 100 * 1024},
                          {8, 32, 256, 4, 100 * 1024},   {8, 16, 256, 4, 100 * 1024},  {4, 16, 256, 4, 100 * 1024},
                          {2, 16, 256, 4, 100 * 1024},   {1, 16, 256, 4, 220 * 1024}};
     const int skip = env_int("WBG_CAS_TILE_SKIP", 0);     // tuning aid: skip the first k candidates
@@ -109,7 +114,7 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
         pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are re-packed
         const long long plane = (long long)rows * pitch;
         // the survivor pool can hold every window of the tile (a round in which nothing is rejected)
-        const int list_cap = c.threads * c.wpt;
+        const int list_cap = std::min(c.threads * c.wpt, c.TR * c.TC);
         const long long bytes = plane * C * 4 + (long long)list_cap * (4 + 2) + 256;
         if (bytes <= c.budget && plane < 65536) {
             g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;

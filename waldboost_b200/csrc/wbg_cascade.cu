@@ -365,6 +365,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 
             }
         }
     } else {
+        // (measured on config C, 10 channels: 8-byte loads with four in flight per thread, flat or row-walking, are
+        // 9-12 % slower than this plain loop -- a thread's C loads share its cache lines with its neighbours')
         for (int i = tid; i < lrows * lcols; i += THREADS) {
             const int rr = i / lcols, cc = i - rr * lcols;
             const float* s = src + ((long long)rr * v + cc) * p.C;

@@ -906,8 +906,14 @@ static int launch_hist_level(const PyrParams& p, int S, int SM, long long grid, 
 // float32 gradients for uint8 images, pooled values converted to float64 once for the smoothing sums.
 // Channels: [0] = gradient magnitude normalised by its 2G+1 triangle average (channels.py:30-37), [1..] = grad_hist
 // bins when p.kind == WBG_CH_GRAD_MAG_HIST.
+// The tile's shared memory (~80 KB with 10 channels) allows two CTAs per SM: 512 threads each keep 32 warps resident,
+// which this latency-bound kernel (sqrt, divisions, float64 conversions on the XU pipe) needs.
+#ifndef WBG_MAG_THREADS
+#define WBG_MAG_THREADS 512
+#endif
+constexpr int MAG_THREADS = WBG_MAG_THREADS;
 template <typename T, int S, int SM, int G>
-__global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams p) {
+__global__ void __launch_bounds__(MAG_THREADS) level_mag_kernel(const PyrParams p) {
     constexpr int TU = PYR_TU, TV = PYR_TV;
     constexpr int PH = TU + 2 * SM, PW = TV + 2 * SM;
     constexpr int FH = S * PH, FW = S * PW;                 // full-resolution channel pixels
@@ -946,7 +952,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
     const int2 mm = p.minmax[(long long)frame * p.n_oct + L->oct];
     const bool identity = L->identity != 0;
 
-    for (int i = tid; i < RH + RW; i += PYR_THREADS) {
+    for (int i = tid; i < RH + RW; i += MAG_THREADS) {
         const bool row = i < RH;
         const Tap t = row ? make_tap(reflect_idx(ry0 + i, nh), L->zoom_r, sh) : make_tap(reflect_idx(rx0 + (i - RH), nw), L->zoom_c, sw);
         TapF f;
@@ -955,7 +961,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
     }
     __syncthreads();
     // ---- resized tile (channels.py:132)
-    for (int i = tid; i < RH * RW; i += PYR_THREADS) {
+    for (int i = tid; i < RH * RW; i += MAG_THREADS) {
         const int iy = i / RW, ix = i - iy * RW;
         const TapF* a = s_tapr + iy;
         const TapF* b = s_tapc + ix;
@@ -998,7 +1004,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
         gy = __fsub_rn(smooth121(r[-RW - 1], r[-RW], r[-RW + 1]), smooth121(r[RW - 1], r[RW], r[RW + 1]));
     };
     // ---- gradient magnitude on the extended grid (channels.py:31-32), float32 throughout
-    for (int i = tid; i < MH * MW; i += PYR_THREADS) {
+    for (int i = tid; i < MH * MW; i += MAG_THREADS) {
         const int iy = i / MW, ix = i - iy * MW;
         float gx, gy;
         grad(s_R + (iy + 1) * RW + ix + 1, gx, gy);
@@ -1011,7 +1017,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
         double tri[G + 1];
 #pragma unroll
         for (int k = 0; k <= G; ++k) tri[k] = (double)p.tri[k];
-        for (int i = tid; i < FH * MW; i += PYR_THREADS) {
+        for (int i = tid; i < FH * MW; i += MAG_THREADS) {
             const int iy = i / MW, ix = i - iy * MW;
             const float* c = s_M + (iy + G) * MW + ix;
             double acc = (double)c[0] * tri[G];
@@ -1020,7 +1026,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
             s_T1[i] = (float)acc;
         }
         __syncthreads();
-        for (int i = tid; i < FH * FW; i += PYR_THREADS) {
+        for (int i = tid; i < FH * FW; i += MAG_THREADS) {
             const int iy = i / FW, ix = i - iy * FW;
             const float* c = s_T1 + iy * MW + ix + G;
             double acc = (double)c[0] * tri[G];
@@ -1029,12 +1035,12 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
             s_F[i] = __fdiv_rn(s_M[(iy + G) * MW + ix + G], __fadd_rn((float)acc, p.eps));
         }
     } else {
-        for (int i = tid; i < FH * FW; i += PYR_THREADS) s_F[i] = s_M[i];
+        for (int i = tid; i < FH * FW; i += MAG_THREADS) s_F[i] = s_M[i];
     }
     __syncthreads();
 
     // ---- channels at full resolution + SxS mean (channels.py:136-139); pooled values as float64
-    for (int i = tid; i < PH * PW; i += PYR_THREADS) {
+    for (int i = tid; i < PH * PW; i += MAG_THREADS) {
         const int py = i / PW, px = i - py * PW;
         const int pu = ou0 - SM + py, pv = ov0 - SM + px;
         if (pu < 0 || pu >= u || pv < 0 || pv >= v) continue;
@@ -1066,10 +1072,15 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
     }
     __syncthreads();
 
-    // ---- 3x3 smoothing with a zero border ring (channels.py:78-90) and the HWC store
+    // ---- 3x3 smoothing with a zero border ring (channels.py:78-90) and the HWC store.  One channel plane at a time with
+    // the lanes of a warp on adjacent columns (conflict-free float64 reads, no run-time divisions); the results are
+    // laid out HWC in shared memory (over the resized tile and the magnitude, both dead by now) so that the global
+    // stores are runs of TV * C contiguous floats per tile row instead of C-strided scatters.
     float* __restrict__ out = p.chns + (long long)frame * p.chn_stride + L->chn_off;
-    for (int i = tid; i < TU * TV * C; i += PYR_THREADS) {
-        const int c = i % C, pix = i / C;
+    const bool stage_out = TU * TV * C <= RH * RW + FH * FW;
+    float* s_out = s_R;                                        // [TU][TV][C]; s_R and s_F are contiguous
+    for (int i = tid; i < TU * TV * C; i += MAG_THREADS) {
+        const int c = i / (TU * TV), pix = i - c * (TU * TV);
         const int oy = pix / TV, ox = pix - oy * TV;
         const int ou = ou0 + oy, ov = ov0 + ox;
         if (ou >= u || ov >= v) continue;
@@ -1090,7 +1101,18 @@ __global__ void __launch_bounds__(PYR_THREADS) level_mag_kernel(const PyrParams 
             a += q[PW + 1];
             r = (float)(a * 0.0625);
         }
-        out[((long long)ou * v + ov) * C + c] = r;
+        if (stage_out) s_out[pix * C + c] = r;
+        else out[((long long)ou * v + ov) * C + c] = r;
+    }
+    if (stage_out) {
+        __syncthreads();
+        const int cols = min(TV, v - ov0), rows = min(TU, u - ou0);
+        const int run = cols * C;                              // contiguous floats per tile row in HBM
+        for (int oy = tid / 32; oy < rows; oy += MAG_THREADS / 32) {
+            float* __restrict__ o = out + ((long long)(ou0 + oy) * v + ov0) * C;
+            const float* __restrict__ srow = s_out + oy * TV * C;
+            for (int j = tid & 31; j < run; j += 32) o[j] = srow[j];
+        }
     }
 }
 
@@ -1111,7 +1133,7 @@ static int launch_mag_level(const PyrParams& p, int S, int SM, int G, long long 
         if (smem > 200 * 1024) { *handled = false; return WBG_OK; }                                                  \
         WBG_CUDA_TRY(cudaFuncSetAttribute(level_mag_kernel<T, SS, MM, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         wbg_prof_begin(WBG_PROF_LEVEL_KERNEL, stream);                                                               \
-        level_mag_kernel<T, SS, MM, GG><<<(unsigned)grid, PYR_THREADS, smem, stream>>>(p);                           \
+        level_mag_kernel<T, SS, MM, GG><<<(unsigned)grid, MAG_THREADS, smem, stream>>>(p);                           \
         wbg_prof_end(WBG_PROF_LEVEL_KERNEL, stream);                                                                 \
         WBG_CUDA_TRY(cudaGetLastError());                                                                            \
         return WBG_OK;                                                                                               \
