@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(PYR_THREADS) level_kernel(const PyrParams p) {
             const int iy = i / MW, ix = i - iy * MW;
             float gx, gy;
             grad(iy + 1, ix + 1, gx, gy);
-            s_M[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+            s_M[i] = (double)__fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
         }
         __syncthreads();
         if (G > 0) {
@@ -937,14 +937,16 @@ __global__ void __launch_bounds__(MAG_THREADS) level_mag_kernel(const PyrParams 
     const bool has_hist = p.kind == WBG_CH_GRAD_MAG_HIST;
     const int ry0 = S * (ou0 - SM) - G - 1, rx0 = S * (ov0 - SM) - G - 1;
 
-    // shared memory: taps | R | F (normalised magnitude) | union { M + T1 (magnitude, first triangle pass), P (pooled, float64) }
+    // shared memory: taps | R | F (normalised magnitude) | union { M + T1 (magnitude, first triangle pass), P (pooled) }.
+    // M, T1 and P hold float32 VALUES widened to float64 once: every element feeds 11 (triangle) or 9 (smoothing)
+    // float64 sums, and a float -> double conversion is a conversion-pipe instruction each time it is repeated.
     TapF* s_tapr = reinterpret_cast<TapF*>(smem_raw);
     TapF* s_tapc = s_tapr + RH;
     float* s_R = reinterpret_cast<float*>(s_tapc + RW);        // [RH][RW]
     float* s_F = s_R + RH * RW;                                // [FH][FW]
-    float* s_M = s_F + FH * FW;                                // [MH][MW]
-    float* s_T1 = s_M + MH * MW;                               // [FH][MW]
-    double* s_P = reinterpret_cast<double*>(s_M);              // [C][PH*PW], written after M / T1 are dead
+    double* s_M = reinterpret_cast<double*>(s_F + FH * FW + ((RH * RW + FH * FW) & 1));   // [MH][MW], 8-byte aligned
+    double* s_T1 = s_M + MH * MW;                              // [FH][MW]
+    double* s_P = s_M;                                         // [C][PH*PW], written after M / T1 are dead
 
     const T* __restrict__ src = (L->oct == 0)
         ? reinterpret_cast<const T*>(p.img) + (long long)frame * p.img_stride
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(MAG_THREADS) level_mag_kernel(const PyrParams 
             bool exact = true;
             val = 0.f;
             if (sizeof(T) == 1) {
-                const float f00 = (float)q00, f01 = (float)q01, f10 = (float)q10, f11 = (float)q11;
+                const float f00 = u8_to_f32((unsigned)q00), f01 = u8_to_f32((unsigned)q01), f10 = u8_to_f32((unsigned)q10), f11 = u8_to_f32((unsigned)q11);
                 const float top = fmaf(b->w1f, f01 - f00, f00), bot = fmaf(b->w1f, f11 - f10, f10);
                 const float r = fmaf(a->w1f, bot - top, top);
                 val = __fadd_rd(r, 12582912.f) - 12582912.f;
@@ -1008,7 +1010,7 @@ __global__ void __launch_bounds__(MAG_THREADS) level_mag_kernel(const PyrParams 
         const int iy = i / MW, ix = i - iy * MW;
         float gx, gy;
         grad(s_R + (iy + 1) * RW + ix + 1, gx, gy);
-        s_M[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+        s_M[i] = (double)__fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
     }
     __syncthreads();
     if (G > 0) {
@@ -1019,23 +1021,23 @@ __global__ void __launch_bounds__(MAG_THREADS) level_mag_kernel(const PyrParams 
         for (int k = 0; k <= G; ++k) tri[k] = (double)p.tri[k];
         for (int i = tid; i < FH * MW; i += MAG_THREADS) {
             const int iy = i / MW, ix = i - iy * MW;
-            const float* c = s_M + (iy + G) * MW + ix;
-            double acc = (double)c[0] * tri[G];
+            const double* c = s_M + (iy + G) * MW + ix;
+            double acc = c[0] * tri[G];
 #pragma unroll
-            for (int k = -G; k < 0; ++k) acc += ((double)c[k * MW] + (double)c[-k * MW]) * tri[G + k];
-            s_T1[i] = (float)acc;
+            for (int k = -G; k < 0; ++k) acc += (c[k * MW] + c[-k * MW]) * tri[G + k];
+            s_T1[i] = (double)(float)acc;                      // float32 between the passes
         }
         __syncthreads();
         for (int i = tid; i < FH * FW; i += MAG_THREADS) {
             const int iy = i / FW, ix = i - iy * FW;
-            const float* c = s_T1 + iy * MW + ix + G;
-            double acc = (double)c[0] * tri[G];
+            const double* c = s_T1 + iy * MW + ix + G;
+            double acc = c[0] * tri[G];
 #pragma unroll
-            for (int k = -G; k < 0; ++k) acc += ((double)c[k] + (double)c[-k]) * tri[G + k];
-            s_F[i] = __fdiv_rn(s_M[(iy + G) * MW + ix + G], __fadd_rn((float)acc, p.eps));
+            for (int k = -G; k < 0; ++k) acc += (c[k] + c[-k]) * tri[G + k];
+            s_F[i] = __fdiv_rn((float)s_M[(iy + G) * MW + ix + G], __fadd_rn((float)acc, p.eps));
         }
     } else {
-        for (int i = tid; i < FH * FW; i += MAG_THREADS) s_F[i] = s_M[i];
+        for (int i = tid; i < FH * FW; i += MAG_THREADS) s_F[i] = (float)s_M[i];
     }
     __syncthreads();
 
@@ -1120,7 +1122,7 @@ template <int S, int SM, int G>
 static constexpr size_t mag_smem_bytes(int C) {
     constexpr int PH = PYR_TU + 2 * SM, PW = PYR_TV + 2 * SM, FH = S * PH, FW = S * PW, MH = FH + 2 * G, MW = FW + 2 * G;
     constexpr int RH = MH + 2, RW = MW + 2;
-    const size_t mt = (size_t)(MH * MW + FH * MW) * 4, pp = (size_t)C * PH * PW * 8;
+    const size_t mt = (size_t)(MH * MW + FH * MW) * 8, pp = (size_t)C * PH * PW * 8;
     return (size_t)(RH + RW) * sizeof(TapF) + (size_t)(RH * RW + FH * FW) * 4 + (mt > pp ? mt : pp) + 32;
 }
 
