@@ -150,7 +150,7 @@ def test_level_sharded_detect_world2_gloo(tmp_path):
     assert tuple(got["stats"]) == tuple(ref_stats)
 
 
-def _pipelined_worker(rank, world, port, out_path):
+def _pipelined_worker(rank, world, port, out_path, big=False):
     import torch.distributed as dist
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
@@ -160,7 +160,7 @@ def _pipelined_worker(rank, world, port, out_path):
     g = sharding.HitGatherer(presorted=True)
     futs = []
     for step in range(4):                               # ragged and empty lists, several steps in flight
-        n = (3 * step + 2 * rank) % 5
+        n = (3 * step + 2 * rank) % 5 + (3000 if big and step == 2 and rank == 1 else 0)
         h = np.zeros(n, HIT_DTYPE)
         h["frame"], h["r"], h["c"], h["score"] = 10 * rank + step, np.arange(n), step, rank + 0.5
         futs.append(g.submit(h, (100 * step + rank, 7)))
@@ -173,15 +173,18 @@ def _pipelined_worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_pipelined_gather_world2_gloo(tmp_path):
-    """HitGatherer: gathers submitted back to back come out per step, in rank order, with the counters summed."""
+@pytest.mark.parametrize("big", [False, True])
+def test_pipelined_gather_world2_gloo(tmp_path, big):
+    """HitGatherer: gathers submitted back to back come out per step, in rank order, with the counters summed.  The first
+    gather of a group takes the general two-collective path, short lists then switch to the one-collective path; with
+    `big` one rank's list overflows that path's fixed buffer in step 2 and every rank falls back together."""
     import torch.multiprocessing as mp
     out = str(tmp_path / "pipe.npz")
-    mp.spawn(_pipelined_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_pipelined_worker, args=(2, _free_port(), out, big), nprocs=2, join=True)
     got = np.load(out)
     for step in range(4):
         h = got[f"hits{step}"]
-        n0, n1 = (3 * step) % 5, (3 * step + 2) % 5
+        n0, n1 = (3 * step) % 5, (3 * step + 2) % 5 + (3000 if big and step == 2 else 0)
         assert h.size == n0 + n1
         assert np.array_equal(h["frame"], [step] * n0 + [10 + step] * n1) and np.array_equal(h["r"], list(range(n0)) + list(range(n1)))
         assert tuple(got["stats"][step]) == (200 * step + 1, 14)

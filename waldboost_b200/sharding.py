@@ -61,6 +61,10 @@ def normalise_hits(hits):
     return hits[order]
 
 
+_FAST_CAP = 1024     # records per rank that the one-collective gather carries
+_LAST_MAX = {}       # per process group: the longest per-rank hit list of the previous gather (the same on every rank)
+
+
 def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
     """Host-side gather of per-rank hit records (frame indices already global) and (n_loc, n_weak) counters.
     Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere.
@@ -83,17 +87,45 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
         parts = [np.frombuffer(b, dtype=np.dtype(d)) for b, d, _ in bucket]
         stats = (sum(s[0] for *_, s in bucket), sum(s[1] for *_, s in bucket))
     else:
-        # host memory, two collectives, no pickling: the counts (and counters) of every rank, then the records padded to
-        # the longest list
         item = local_hits.dtype.itemsize
-        hdr = torch.tensor([int(local_hits.size), int(local_stats[0]), int(local_stats[1])], dtype=torch.int64)
-        all_hdr = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(all_hdr, hdr, group=group)
+        hdr_np = np.array([int(local_hits.size), int(local_stats[0]), int(local_stats[1])], np.int64)
+        raw = np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1)
+        key = id(group) if group is not None else 0
+        all_hdr = None
+        if _LAST_MAX.get(key, _FAST_CAP) <= _FAST_CAP // 2:
+            # short lists (the previous gather of this group, whose counts every rank saw, stayed well under the cap):
+            # ONE collective -- every rank sends a fixed-size buffer [count, n_loc, n_weak | records]; every rank also
+            # receives all of them, so all ranks agree on whether a list overflowed and the general path must run
+            buf = torch.zeros(24 + _FAST_CAP * item, dtype=torch.uint8)
+            buf[:24] = torch.from_numpy(hdr_np.view(np.uint8))
+            k = min(raw.size, _FAST_CAP * item)
+            if k:
+                buf[24:24 + k] = torch.from_numpy(raw[:k])
+            bucket = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(bucket, buf, group=group)
+            all_hdr = [b.numpy()[:24].view(np.int64) for b in bucket]
+            counts = [int(h[0]) for h in all_hdr]
+            _LAST_MAX[key] = max(counts)
+            if max(counts) <= _FAST_CAP:
+                if rank != dst:
+                    return None, None
+                parts = [b.numpy()[24:24 + c * item].view(local_hits.dtype) for b, c in zip(bucket, counts)]
+                stats = (sum(int(h[1]) for h in all_hdr), sum(int(h[2]) for h in all_hdr))
+                hits = np.concatenate(parts) if parts else local_hits
+                return (hits if presorted else normalise_hits(hits)), stats
+        # general path -- host memory, two collectives, no pickling: the counts (and counters) of every rank, then the
+        # records padded to the longest list
+        if all_hdr is None:
+            hdr = torch.from_numpy(hdr_np)
+            all_t = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(all_t, hdr, group=group)
+            all_hdr = [t.numpy() for t in all_t]
         counts = [int(h[0]) for h in all_hdr]
+        _LAST_MAX[key] = max(counts)
         cap = max(max(counts), 1) * item
         buf = torch.zeros(cap, dtype=torch.uint8)
-        if local_hits.size:
-            buf[:local_hits.size * item] = torch.from_numpy(np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1))
+        if raw.size:
+            buf[:raw.size] = torch.from_numpy(raw)
         bucket = [torch.empty(cap, dtype=torch.uint8) for _ in range(world)] if rank == dst else None
         dist.gather(buf, bucket, dst=dst, group=group)
         if rank != dst:
