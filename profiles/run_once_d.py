@@ -1,4 +1,4 @@
-"""Small fixed workload for ncu captures of the depth-4 cascade path (config D shape): 8 synthetic 640x480 frames, 2048-stage
+"""Small fixed workload for ncu captures of the depth-4 cascade path (config D shape): 32 synthetic 640x480 frames, 2048-stage
 depth-4 model calibrated like profiles/run_configs.py."""
 import os
 import sys
@@ -14,7 +14,7 @@ from waldboost_b200 import synthetic as S
 from run_configs import calibrated_model
 
 opts = dict(shrink=2, n_per_oct=8, smooth=1, channels=wb.channels.grad_hist)
-frames = S.synthetic_frames(8, 480, 640)
+frames = S.synthetic_frames(32, 480, 640)
 M = calibrated_model((12, 12, 4), opts, 2048, 4, frames[0], 1e-4)
 for _ in range(2):
     M.reset()

@@ -409,7 +409,7 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 extern "C" void wbg_model_destroy(wbg_model* m) {
     if (!m) return;
     cudaFree(m->d_feature); cudaFree(m->d_threshold); cudaFree(m->d_left); cudaFree(m->d_right);
-    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_dk4);
+    cudaFree(m->d_prediction); cudaFree(m->d_theta); cudaFree(m->d_nodes); cudaFree(m->d_d2); cudaFree(m->d_dk4); cudaFree(m->d_dk4root);
     delete m;
 }
 
@@ -534,6 +534,12 @@ extern "C" int wbg_model_create(const wbg_model_desc* d, wbg_model** out) {
         if (e == cudaSuccess) e = upload(&m->d_nodes, nodes.data(), TN);
         if (e == cudaSuccess && all_d2) e = upload(&m->d_d2, d2.data(), (size_t)T);
         if (e == cudaSuccess && all_dk4) e = upload(&m->d_dk4, dk4.data(), (size_t)T);
+        if (e == cudaSuccess && all_dk4 && T <= DK4_MAX_ROOT_STAGES) {
+            std::vector<int4> roots((size_t)T);
+            for (int t = 0; t < T; ++t)
+                roots[t] = make_int4(dk4[t].node[0].x, dk4[t].node[0].y, __builtin_bit_cast(int, dk4[t].theta), 0);
+            e = upload(&m->d_dk4root, roots.data(), (size_t)T);
+        }
     }
     if (e != cudaSuccess) {
         wbg_set_error("wbg_model_create: no usable CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));

@@ -42,7 +42,11 @@
 #define WBG_DEV_ASSERT(c) ((void)0)
 #endif
 
-__constant__ StageD2 c_d2[D2_MAX_STAGES];
+// One constant bank per device, used by whichever model ran last (see BankState below): the depth-2 stage records
+// (three 16-byte groups per stage) or, for depth-4 models, the warp-uniform part of their stages (root node + theta,
+// one 16-byte entry per stage) so that those reads go through the uniform datapath instead of shared memory.
+__constant__ int4 c_bank[D2_MAX_STAGES * 3];
+static_assert(sizeof(StageD2) == 3 * sizeof(int4), "StageD2 is three 16-byte groups");
 
 constexpr int WBG_DBG_TILES = 16384;     // tiles covered by the per-tile debug log
 
@@ -126,7 +130,8 @@ __device__ __forceinline__ float fset_le(float a, float b) { float d; asm("set.l
 __device__ __forceinline__ float fset_gtu(float a, float b) { float d; asm("set.gtu.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }   // !(a <= b)
 __device__ __forceinline__ float fset_ge(float a, float b) { float d; asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 
-enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2 };
+enum { MODE_GENERIC = 0, MODE_D2 = 1, MODE_DK4 = 2, MODE_DK4C = 3 };   // DK4C: depth-4 records whose root and theta come from the constant bank
+#define IS_DK4(MODE) ((MODE) == MODE_DK4 || (MODE) == MODE_DK4C)
 constexpr int DK4_ROUND_MAX = 64;   // stages per round of the depth-4 path: their records (12 KB) are staged in shared memory
 #ifndef D2_DEPENDENT_MIN_NK
 #define D2_DEPENDENT_MIN_NK 2       // slots per thread from which the depth-2 path gathers only the taken child
@@ -137,7 +142,8 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
                                           int t, int t_end, unsigned& my_weak, const NodeDev* __restrict__ nodes, int N,
                                           const float* __restrict__ thetas, const StageDK4* __restrict__ dk4) {
     constexpr bool D2 = MODE == MODE_D2;
-    if (MODE == MODE_DK4) {
+    if (IS_DK4(MODE)) {
+        constexpr bool DK4_ROOT_CONST = MODE == MODE_DK4C;
         // complete depth-4 stages in heap order.  The records of the round were staged in shared memory (rec_base): the
         // root and theta are broadcast reads, levels 1..3 and the leaf are lane-dependent 8- / 4-byte reads with at
         // most 2 / 4 / 8 / 16 distinct addresses per warp.  Every load is unconditional, so there is no divergence and
@@ -153,8 +159,16 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 #pragma unroll kDk4Unroll
         for (int s = t; s < t_end; ++s) {
             const unsigned rec = rec_base + (unsigned)(s - t) * (unsigned)sizeof(StageDK4);
-            const float2 root = lds_v2(rec);
-            const float theta = lds_f32v(rec + 120u);
+            float2 root;
+            float theta;
+            if (DK4_ROOT_CONST) {
+                const int4 R = c_bank[s];                      // uniform datapath: two shared-memory reads less per stage
+                root = make_float2(__int_as_float(R.x), __int_as_float(R.y));
+                theta = __int_as_float(R.z);
+            } else {
+                root = lds_v2(rec);
+                theta = lds_f32v(rec + 120u);
+            }
             unsigned nd_addr[NK];                   // address of the current node record; node i sits at rec + 8 i
 #pragma unroll
             for (int k = 0; k < NK; ++k)
@@ -197,9 +211,9 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
         for (int s = t; s < t_end; ++s) {
             // offsets, theta and thresholds are only ever used as uniform operands; the four leaves are selected
             // between per lane and are read as one 16-byte constant load into vector registers
-            const int4* __restrict__ rec = reinterpret_cast<const int4*>(&c_d2[s]);
+            const int4* __restrict__ rec = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(c_bank) + s * (int)sizeof(StageD2));
             const int4 A = rec[0], B = rec[1];
-            const float4 Lf = *reinterpret_cast<const float4*>(&c_d2[s].p2);
+            const float4 Lf = *reinterpret_cast<const float4*>(rec + 2);
             const float theta = __int_as_float(A.w);
             const float thr0 = __int_as_float(B.x), thr1 = __int_as_float(B.y), thr4 = __int_as_float(B.z);
             const float p2 = Lf.x, p3 = Lf.y, p5 = Lf.z, p6 = Lf.w;
@@ -307,7 +321,7 @@ __device__ __forceinline__ void mark_survivor(const CascadeParams& p, int frame,
 }
 
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 4 : 5) : THREADS == 384 ? (MODE == MODE_DK4 ? 3 : 4) : (MODE == MODE_DK4 ? CAS_MINB_DK4 : CAS_MINB_512x4)) cascade_pool_kernel(const CascadeParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 5) : THREADS == 384 ? (IS_DK4(MODE) ? 3 : 4) : (IS_DK4(MODE) ? CAS_MINB_DK4 : CAS_MINB_512x4)) cascade_pool_kernel(const CascadeParams p) {
     constexpr int WARPS = THREADS / 32;
     constexpr int WPT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -379,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 
     unsigned tile_base = (unsigned)__cvta_generic_to_shared(tile);
     asm volatile("" : "+r"(tile_base) :: "memory");     // patch loads may not be hoisted above the barrier
 
-    const int aux = MODE == MODE_DK4 ? (int)((unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)p.rec_off) : p.N;
+    const int aux = IS_DK4(MODE) ? (int)((unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)p.rec_off) : p.N;
     unsigned wa[WPT] = {0, 0, 0, 0};
     float hs[WPT] = {0.f, 0.f, 0.f, 0.f}, alive[WPT] = {0.f, 0.f, 0.f, 0.f};
     int n = nwin, t = 0, par = 0;
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 
             if (warp != 0) break;
             while (t < p.T) {
                 int te = min(p.T, t + p.round_solo);
-                if (MODE == MODE_DK4) {
+                if (IS_DK4(MODE)) {
                     te = min(te, t + DK4_ROUND_MAX);
                     const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t);
                     int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (MODE == MODE_DK4 ? 
         }
         if (pooled) __syncthreads();                  // every slot is in registers before the pool is overwritten
         int t_end = min(p.T, t + (n > p.round_n1 ? p.round_full : (n > p.round_n2 ? p.round_mid : p.round_tail)));
-        if (MODE == MODE_DK4) {
+        if (IS_DK4(MODE)) {
             t_end = min(t_end, t + DK4_ROUND_MAX);
             const int4* __restrict__ g = reinterpret_cast<const int4*>(p.dk4 + t);
             int4* d = reinterpret_cast<int4*>(smem_raw + p.rec_off);
@@ -659,7 +673,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) emit_hits(const EmitParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Ownership of the constant bank that holds the depth-2 stage table (c_d2), per device.
+// Ownership of the constant bank (c_bank: the depth-2 stage table or a depth-4 model's root table), per device.
 constexpr int WBG_MAX_DEVICES = 64;
 struct BankUser { cudaStream_t stream; cudaEvent_t done; };
 struct BankState {
@@ -773,15 +787,20 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
     // made to wait for the last cascade launched on every other stream (they may still read the old table), and
     // launches on other streams wait for the copy's event.  The lock is held until the kernel is enqueued, so two
     // host threads with different models cannot interleave "load table" and "launch".
+    const bool dk4_const = use_dk4 && model->d_dk4root != nullptr && !getenv("WBG_CAS_DK4_SMEM_ROOT");
+    const bool uses_bank = model->all_d2 || dk4_const;
     std::unique_lock<std::mutex> bank_lock(g_bank_mutex, std::defer_lock);
-    if (model->all_d2) {
+    if (uses_bank) {
         bank_lock.lock();
         const int dev = model->device >= 0 && model->device < WBG_MAX_DEVICES ? model->device : 0;
         BankState& bs = g_bank[dev];
         if (bs.owner != model->uid) {
             for (auto& u : bs.users)
                 if (u.stream != stream) WBG_CUDA_TRY(cudaStreamWaitEvent(stream, u.done, 0));
-            WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_d2, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
+            if (model->all_d2)
+                WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_bank, model->d_d2, sizeof(StageD2) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
+            else
+                WBG_CUDA_TRY(cudaMemcpyToSymbolAsync(c_bank, model->d_dk4root, sizeof(int4) * (size_t)model->T, 0, cudaMemcpyDeviceToDevice, stream));
             if (!bs.ready) WBG_CUDA_TRY(cudaEventCreateWithFlags(&bs.ready, cudaEventDisableTiming));
             WBG_CUDA_TRY(cudaEventRecord(bs.ready, stream));
             bs.ready_stream = stream;
@@ -808,6 +827,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
 #define WBG_CAS_LAUNCH_POOL(TH)                                                                               \
     do {                                                                                                      \
         if (model->all_d2) WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_D2, TH>), TH);                          \
+        else if (dk4_const) WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_DK4C, TH>), TH);                       \
         else if (use_dk4) WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_DK4, TH>), TH);                          \
         else WBG_CAS_LAUNCH_K((cascade_pool_kernel<MODE_GENERIC, TH>), TH);                                   \
     } while (0)
@@ -817,7 +837,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
     else WBG_CAS_LAUNCH_POOL(256);
 #undef WBG_CAS_LAUNCH_POOL
 #undef WBG_CAS_LAUNCH_K
-    if (model->all_d2) {
+    if (uses_bank) {
         // remember that this stream reads the bank: a later table switch on another stream waits for this event
         const int dev = model->device >= 0 && model->device < WBG_MAX_DEVICES ? model->device : 0;
         BankState& bs = g_bank[dev];

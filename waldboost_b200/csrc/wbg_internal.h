@@ -118,6 +118,7 @@ struct __align__(16) StageDK4 {
     float leaf[16];
 };
 static_assert(sizeof(StageDK4) == 192, "StageDK4 layout");
+constexpr int DK4_MAX_ROOT_STAGES = D2_MAX_STAGES * 3;   // 16-byte root entries that fit the constant bank of the depth-2 table
 
 struct wbg_model {
     unsigned long long uid = 0;   // unique per created model (never reused): identifies the owner of the constant bank
@@ -136,6 +137,7 @@ struct wbg_model {
     StageD2* d_d2 = nullptr;      // [T] when all_d2
     bool all_dk4 = false;         // every stage fits a complete depth-4 tree (and the model is not all_d2)
     StageDK4* d_dk4 = nullptr;    // [T] when all_dk4
+    int4* d_dk4root = nullptr;    // [T] {root offset, root threshold bits, theta bits, 0}: the warp-uniform part of d_dk4 for the constant bank
 };
 
 // ------------------------------------------------------------------------------------------------ profiling hooks
