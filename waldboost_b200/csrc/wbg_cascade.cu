@@ -4,14 +4,13 @@
 // (waldboost/training.py:84-96) and Model.get_boxes (waldboost/model.py:136-147) for every level of every frame
 // of a batch in one launch family:
 //
-//   cascade_kernel   one CTA per tile of TR x TC windows (32 x 64 for the 12x12x4 model).  The (TR+m-1) x (TC+n-1) x C
-//                    channel patch is staged once in shared memory, channel-planar, so that the 32 lanes of a warp
-//                    (adjacent windows) gather adjacent words.  Every thread owns WPT window slots.  The cascade
-//                    runs in rounds of 32..128 stages: within a round each warp scores its slots on its own, stage
-//                    by stage in float32 (stage order, like `hs += weak.predict_on_image`) with the test
-//                    `hs >= theta[t]`; a rejected slot just carries alive = 0 and stops mattering.  At the
-//                    end of a round the CTA counts its survivors and, once no more than 3/4 of the slots are live,
-//                    re-packs them (ballot + prefix sum, order preserving) so rejection does not leave idle lanes.
+//   cascade_pool_kernel  one CTA per tile of TR x TC windows (32 x 64 for the 12x12x4 model).  The (TR+m-1) x (TC+n-1)
+//                    x C channel patch is staged once in shared memory, channel-planar, so that the 32 lanes of a
+//                    warp (adjacent windows) gather adjacent words.  The cascade runs in rounds of 32..128 stages:
+//                    within a round each warp scores its window slots on its own, stage by stage in float32 (stage
+//                    order, like `hs += weak.predict_on_image`) with the test `hs >= theta[t]`; a rejected slot just
+//                    carries alive = 0 and stops mattering.  After every round the survivors go to a pool in shared
+//                    memory and the next round reads them back as full rows of 32 windows (see the kernel).
 //                    Survivors of all T stages set a bit in a per-frame window mask and store their score in a
 //                    dense score map.
 //   mask_*/emit_hits popcount prefix sums over the mask give every survivor its rank in the reference's output
@@ -301,7 +300,7 @@ __device__ __forceinline__ void run_round(unsigned tile_base, const unsigned (&w
 #define CAS_MINB_DK4 2              // the staged depth-4 records leave room for two 512-thread CTAs per SM: 64 registers, no spills
 #endif
 // ------------------------------------------------------------------------------------------------ pool kernel
-// Same tile, patch and stage loops as cascade_kernel, different bookkeeping between rounds: after EVERY round the
+// Bookkeeping between rounds: after EVERY round the
 // survivors of the CTA are appended to a pool in shared memory (window offset + running score; one shared-memory
 // atomicAdd per warp reserves the range, the order inside the pool is irrelevant because hits are ranked from the
 // window mask afterwards).  The next round reads the pool back as full rows of 32 windows, `nk` rows per warp, so
