@@ -114,11 +114,14 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
         pitch += (pitch % 2 == 0);  // odd pitch spreads rows over banks once windows are re-packed
         const long long plane = (long long)rows * pitch;
         // the survivor pool can hold every window of the tile (a round in which nothing is rejected)
-        const int list_cap = std::min(c.threads * c.wpt, c.TR * c.TC);
+        // class-ordered pool: 32 columns (shared-memory bank class of the window origin) of class_cap entries each; a
+        // class has at most TR * ceil(TC / 32) windows in a tile, and an odd column pitch spreads the columns over banks
+        const int class_cap = (c.TR * ((c.TC + 31) / 32)) | 1;
+        const int list_cap = 32 * class_cap;
         const long long bytes = plane * C * 4 + (long long)list_cap * (4 + 2) + 256;
         if (bytes <= c.budget && plane < 65536) {
             g->TR = c.TR; g->TC = c.TC; g->rows = rows; g->pitch = pitch; g->plane = (int)plane;
-            g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap;
+            g->smem_bytes = (int)bytes; g->threads = c.threads; g->wpt = c.wpt; g->list_cap = list_cap; g->class_cap = class_cap;
             g->round_full = env_int("WBG_CAS_ROUND_FULL", 32);
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);

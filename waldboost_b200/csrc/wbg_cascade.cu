@@ -61,7 +61,7 @@ struct CascadeParams {
     int N, T;
     int C, m, n;
     int TR, TC, pitch, plane;
-    int list_cap, round_solo, round_full, round_mid, round_tail, pack;
+    int list_cap, class_cap, round_solo, round_full, round_mid, round_tail, pack;
     int round_n1, round_n2;  // pool kernel: round_full stages while more than round_n1 windows are left, round_mid above round_n2
     unsigned long long* dbg; // debug counters (wbg_cascade_counters_enable), else null
     int rec_off;             // byte offset of the staged stage records inside the dynamic shared memory (MODE_DK4)
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 
     float* pool_hs = tile + ((p.C * p.plane + 3) & ~3);
     unsigned short* pool_wo = reinterpret_cast<unsigned short*>(pool_hs + p.list_cap);
     __shared__ int s_tail[2];
+    __shared__ int s_cnt[2][32];                  // survivors per bank class of the round being written / read
     __shared__ int s_t;                           // stage reached by the tile: re-read after every round's barrier so that the
                                                   // compiler sees a CTA-uniform value (stage records through the uniform datapath)
 
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 
     const int lrows = rows_valid + p.m - 1, lcols = cols_valid + p.n - 1;
     const int pitch = p.pitch, plane = p.plane;
     if (tid < 2) s_tail[tid] = 0;
+    if (tid < 64) (&s_cnt[0][0])[tid] = 0;
     const long long dbg_t0 = p.dbg ? clock64() : 0;
 
     // ---- stage the channel patch, HWC in HBM -> planar in shared memory
@@ -406,23 +408,58 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 
         nk = min(min(max(nk, p.pack), rows), WPT);
         const int row0 = warp * nk;
         // (a warp without rows skips the slot bookkeeping of the round; it only takes part in the barriers)
-        if (row0 < rows || !pooled)
-#pragma unroll
-        for (int k = 0; k < WPT; ++k) {
-            const int idx = (row0 + k) * 32 + lane;
-            const bool has = k < nk && idx < n;
+        if (row0 < rows || !pooled) {
             if (!pooled) {
-                // every window of the tile starts alive with score 0 (model.py:243-247); row-major, so the lanes of a
-                // warp gather adjacent shared-memory words
-                const int lr = has ? idx / cols_valid : 0, lc = has ? idx - lr * cols_valid : 0;
-                wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
-                hs[k] = 0.f;
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) {
+                    // every window of the tile starts alive with score 0 (model.py:243-247); row-major, so the lanes of
+                    // a warp gather adjacent shared-memory words
+                    const int idx = (row0 + k) * 32 + lane;
+                    const bool has = k < nk && idx < n;
+                    const int lr = has ? idx / cols_valid : 0, lc = has ? idx - lr * cols_valid : 0;
+                    wa[k] = tile_base + 4u * (unsigned)(lr * pitch + lc);
+                    hs[k] = 0.f;
+                    alive[k] = has ? 1.f : 0.f;
+                }
             } else {
-                WBG_DEV_ASSERT(!has || (idx >= 0 && idx < p.list_cap));
-                wa[k] = tile_base + 4u * (has ? (unsigned)pool_wo[idx] : 0u);
-                hs[k] = has ? pool_hs[idx] : 0.f;
+                // The pool is ordered by bank class (one column per class).  Reading that order TRANSPOSED -- position
+                // q = lane * rows + row of the class-sorted sequence -- deals every class out over consecutive rows,
+                // so a row of 32 windows holds ceil(count / rows) <= 2 windows of a class where a random row holds
+                // ~3.5: the gathers of the sparse rounds, which are bound by shared-memory wavefronts, cost about a
+                // third less.  Class prefix sums by warp scan, the class of a position by a 5-step shuffle search.
+                const int cnt = s_cnt[par ^ 1][lane];
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const int excl = incl - cnt;
+#pragma unroll
+                for (int k = 0; k < WPT; ++k) {
+                    wa[k] = tile_base;
+                    hs[k] = 0.f;
+                    alive[k] = 0.f;
+                    if (k < nk && row0 + k < rows) {                   // warp-uniform: the shuffles below are convergent
+                        const int q = lane * rows + row0 + k;
+                        const bool has = q < n;
+                        const int qq = has ? q : 0;
+                        int cls = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const int probe = __shfl_sync(0xffffffffu, incl, cls + step - 1);
+                            if (probe <= qq) cls += step;
+                        }
+                        const int e = cls * p.class_cap + (qq - __shfl_sync(0xffffffffu, excl, cls));
+                        WBG_DEV_ASSERT(!has || (e >= 0 && e < p.list_cap));
+                        if (has) {
+                            wa[k] = tile_base + 4u * (unsigned)pool_wo[e];
+                            hs[k] = pool_hs[e];
+                            alive[k] = 1.f;
+                        }
+                    }
+                }
             }
-            alive[k] = has ? 1.f : 0.f;
         }
         if (solo) {
             // at most 32 windows are left: warp 0 finishes the cascade on its own, nobody meets at a barrier any more
@@ -465,26 +502,21 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 
         if (t >= p.T) break;
         // ---- append the survivors to the pool (unordered across warps, one atomic per warp)
         if (row0 < rows) {
-            unsigned bal[WPT];
-            int wcnt = 0;
-#pragma unroll
-            for (int k = 0; k < WPT; ++k) {
-                bal[k] = __ballot_sync(0xffffffffu, alive[k] != 0.f);
-                wcnt += __popc(bal[k]);
-            }
-            int base = 0;
-            if (lane == 0 && wcnt) base = atomicAdd(&s_tail[par], wcnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
+            int mine = 0;
 #pragma unroll
             for (int k = 0; k < WPT; ++k) {
                 if (alive[k] != 0.f) {
-                    const int pos = base + __popc(bal[k] & ((1u << lane) - 1u));
-                    WBG_DEV_ASSERT(pos >= 0 && pos < p.list_cap && ((wa[k] - tile_base) >> 2) < (unsigned)p.plane);
-                    pool_wo[pos] = (unsigned short)((wa[k] - tile_base) >> 2);
-                    pool_hs[pos] = hs[k];
+                    const unsigned wo = (wa[k] - tile_base) >> 2;
+                    const int cls = (int)(wo & 31u);
+                    const int e = cls * p.class_cap + atomicAdd(&s_cnt[par][cls], 1);     // a column per bank class
+                    WBG_DEV_ASSERT(e >= 0 && e < (cls + 1) * p.class_cap && wo < (unsigned)p.plane);
+                    pool_wo[e] = (unsigned short)wo;
+                    pool_hs[e] = hs[k];
+                    ++mine;
                 }
-                base += __popc(bal[k]);
             }
+            const int wcnt = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0 && wcnt) atomicAdd(&s_tail[par], wcnt);
             if (p.dbg && lane == 0) atomicAdd(p.dbg + 6, (unsigned long long)wcnt);
         }
         if (tid == 0) s_t = t;
@@ -492,7 +524,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? (IS_DK4(MODE) ? 4 : 
         n = s_tail[par];
         t = s_t;
         if (tid == 0) s_tail[par ^ 1] = 0;
-        par ^= 1;
+        if (tid < 32) s_cnt[par ^ 1][tid] = 0;
+        par ^= 1;                                     // the round just written is read as s_cnt[par ^ 1] from here on
         pooled = true;
         solo = n <= 32;
 #pragma unroll
@@ -772,7 +805,7 @@ int wbg_launch_cascade(const wbg_model* model, const LevelDev* d_levels, const u
     const long long grid = (long long)tiles_per_frame * batch;
     WBG_REQUIRE(grid <= 0x7fffffffLL, "cascade: too many tiles (%lld)", grid);
     const CascadeGeom& g = model->geom;
-    p.list_cap = g.list_cap; p.round_solo = g.round_solo < 1 ? 1 : g.round_solo;
+    p.list_cap = g.list_cap; p.class_cap = g.class_cap; p.round_solo = g.round_solo < 1 ? 1 : g.round_solo;
     p.round_full = g.round_full; p.round_mid = g.round_mid; p.round_tail = g.round_tail;
     const bool use_dk4_req = !model->all_d2 && model->all_dk4 && !getenv("WBG_CAS_GENERIC");
     p.rec_off = (g.smem_bytes + 15) & ~15;

@@ -45,7 +45,8 @@ struct CascadeGeom {
     int plane;         // floats per channel plane
     int smem_bytes;    // dynamic shared memory of the cascade kernel
     int threads, wpt;  // CTA size and window slots per thread: threads * wpt >= TR * TC
-    int list_cap;      // capacity of the survivor pool (windows): threads * wpt
+    int list_cap;      // capacity of the survivor pool (windows): 32 class columns of class_cap entries
+    int class_cap;
     int round_solo;                 // stages between liveness checks of the last warp of a tile (at most 32 windows left)
     int round_full, round_mid, round_tail;   // stages per round while slots > threads / > 64 / else
     int round_n1, round_n2;                  // pool kernel: window counts that separate round_full / round_mid / round_tail
