@@ -612,7 +612,9 @@ constexpr int H4_PH = H4_TU + 2, H4_PW = H4_TV + 2, H4_RH = 2 * H4_PH + 2, H4_RW
 static_assert(H4_RW == 64, "a resized tile row must be two warp-wide chunks");
 static_assert(H4_TU == PYR_QTU && H4_TV == PYR_QTV, "the plan counts the tiles of this kernel with PYR_QTU x PYR_QTV");
 
-__device__ __forceinline__ float u8_to_f32(unsigned q) { return __int_as_float(0x4B000000u | q) - 8388608.f; }
+// uint8 -> float32: the 32-bit integer conversion (I2FP, an ordinary ALU instruction; 8- and 16-bit conversions go to
+// the slow conversion pipe) -- and the compiler converts a difference of two taps once instead of both taps
+__device__ __forceinline__ float u8_to_f32(unsigned q) { return __int2float_rn((int)q); }
 
 // cos(pi/4) of the reference's orientation table (np.cos(np.linspace(0, pi, 5)[1]) = 0x1.6a09e667f3bcdp-1) as two float32:
 // for the integer gradients of a uint8 image, fma(d, C_HI, d * C_LO) with d = gx - gy (bin 1) or gx + gy (bin 3) equals
@@ -717,6 +719,8 @@ __global__ void __launch_bounds__(H4_THREADS, H4_MINB) level_hist4_u8_kernel(con
             if (identity) {
                 val = u8_to_f32(__ldg(r0p + bi0));
             } else {
+                // (one shared address for the two column taps when they are adjacent bytes -- nearly always -- was tried:
+                // the warp-uniform branch and the duplicated loads cost more than the two address computations, 5.51 vs 5.28 ms)
                 const unsigned q00 = __ldg(r0p + bi0), q01 = __ldg(r0p + bi1), q10 = __ldg(r1p + bi0), q11 = __ldg(r1p + bi1);
                 const float f00 = u8_to_f32(q00), f01 = u8_to_f32(q01), f10 = u8_to_f32(q10), f11 = u8_to_f32(q11);
                 const float wx = (task & 1) ? c1w : c0w, wy = a->w1f;
