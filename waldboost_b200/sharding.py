@@ -62,14 +62,24 @@ def normalise_hits(hits):
 
 
 _FAST_CAP = 1024     # records per rank that the one-collective gather carries
-_LAST_MAX = {}       # per process group: the longest per-rank hit list of the previous gather (the same on every rank)
 
 
-def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
+class GatherState:
+    """What consecutive gathers over one process group remember: the longest per-rank hit list of the previous gather.
+    Every rank sees every count in each gather, so the value -- and with it the choice between the one-collective and
+    the general path -- is the same on all ranks PROVIDED all ranks create the object at the same point and pass it to
+    the same sequence of gather_hits calls (HitGatherer does)."""
+
+    def __init__(self):
+        self.last_max = None
+
+
+def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False, state=None):
     """Host-side gather of per-rank hit records (frame indices already global) and (n_loc, n_weak) counters.
     Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere.
     `presorted`: every rank's list is already in that order and the ranks hold ascending frame ranges (image
-    sharding), so concatenating in rank order needs no sort."""
+    sharding), so concatenating in rank order needs no sort.  `state`: a GatherState shared by a sequence of calls
+    (the same on every rank); with it, short lists travel in one collective instead of two."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return (local_hits if presorted else normalise_hits(local_hits)), tuple(int(x) for x in local_stats)
@@ -90,9 +100,8 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
         item = local_hits.dtype.itemsize
         hdr_np = np.array([int(local_hits.size), int(local_stats[0]), int(local_stats[1])], np.int64)
         raw = np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1)
-        key = id(group) if group is not None else 0
         all_hdr = None
-        if _LAST_MAX.get(key, _FAST_CAP) <= _FAST_CAP // 2:
+        if state is not None and state.last_max is not None and state.last_max <= _FAST_CAP // 2:
             # short lists (the previous gather of this group, whose counts every rank saw, stayed well under the cap):
             # ONE collective -- every rank sends a fixed-size buffer [count, n_loc, n_weak | records]; every rank also
             # receives all of them, so all ranks agree on whether a list overflowed and the general path must run
@@ -105,7 +114,7 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
             dist.all_gather(bucket, buf, group=group)
             all_hdr = [b.numpy()[:24].view(np.int64) for b in bucket]
             counts = [int(h[0]) for h in all_hdr]
-            _LAST_MAX[key] = max(counts)
+            state.last_max = max(counts)
             if max(counts) <= _FAST_CAP:
                 if rank != dst:
                     return None, None
@@ -121,7 +130,8 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
             dist.all_gather(all_t, hdr, group=group)
             all_hdr = [t.numpy() for t in all_t]
         counts = [int(h[0]) for h in all_hdr]
-        _LAST_MAX[key] = max(counts)
+        if state is not None:
+            state.last_max = max(counts)
         cap = max(max(counts), 1) * item
         buf = torch.zeros(cap, dtype=torch.uint8)
         if raw.size:
@@ -145,10 +155,12 @@ class HitGatherer:
     def __init__(self, group=None, dst=0, presorted=False):
         from concurrent.futures import ThreadPoolExecutor
         self.group, self.dst, self.presorted = group, dst, presorted
+        self.state = GatherState()
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="wbg-gather")
 
     def submit(self, local_hits, local_stats):
-        return self._pool.submit(gather_hits, local_hits, tuple(int(x) for x in local_stats), self.group, self.dst, self.presorted)
+        return self._pool.submit(gather_hits, local_hits, tuple(int(x) for x in local_stats), self.group, self.dst, self.presorted,
+                                 self.state)
 
     def close(self):
         self._pool.shutdown(wait=True)
