@@ -413,7 +413,6 @@ def run_config_c(args):
     import waldboost_b200 as wb
     from waldboost_b200 import sharding, synthetic as S
     from waldboost_b200.engine import cascade_tile, get_engine, plan_geometry
-    gather_state = sharding.GatherState()       # created at the same point on every rank: short lists gather in one collective
 
     def barrier():
         if world > 1:
@@ -439,7 +438,7 @@ def run_config_c(args):
         ta = time.perf_counter()
         _, h = model.detect_batch(frame, return_hits=True, bands=mine)
         t_detect[0] += time.perf_counter() - ta
-        return sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0, state=gather_state)
+        return sharding.gather_hits(h, (model.n_loc, model.n_weak), group=host_group, dst=0)
 
     for _ in range(max(args.warmup, 3)):
         hits, stats = step()

@@ -175,9 +175,8 @@ def _pipelined_worker(rank, world, port, out_path, big=False):
 
 @pytest.mark.parametrize("big", [False, True])
 def test_pipelined_gather_world2_gloo(tmp_path, big):
-    """HitGatherer: gathers submitted back to back come out per step, in rank order, with the counters summed.  The first
-    gather of a group takes the general two-collective path, short lists then switch to the one-collective path; with
-    `big` one rank's list overflows that path's fixed buffer in step 2 and every rank falls back together."""
+    """HitGatherer: gathers submitted back to back come out per step, in rank order, with the counters summed; with `big`
+    one rank's list is three orders of magnitude longer than the others' in one step (padding to the longest list)."""
     import torch.multiprocessing as mp
     out = str(tmp_path / "pipe.npz")
     mp.spawn(_pipelined_worker, args=(2, _free_port(), out, big), nprocs=2, join=True)

@@ -61,25 +61,11 @@ def normalise_hits(hits):
     return hits[order]
 
 
-_FAST_CAP = 1024     # records per rank that the one-collective gather carries
-
-
-class GatherState:
-    """What consecutive gathers over one process group remember: the longest per-rank hit list of the previous gather.
-    Every rank sees every count in each gather, so the value -- and with it the choice between the one-collective and
-    the general path -- is the same on all ranks PROVIDED all ranks create the object at the same point and pass it to
-    the same sequence of gather_hits calls (HitGatherer does)."""
-
-    def __init__(self):
-        self.last_max = None
-
-
-def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False, state=None):
+def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False):
     """Host-side gather of per-rank hit records (frame indices already global) and (n_loc, n_weak) counters.
     Returns (hits ordered by (frame, level, r, c), (n_loc, n_weak)) on rank `dst`, (None, None) elsewhere.
     `presorted`: every rank's list is already in that order and the ranks hold ascending frame ranges (image
-    sharding), so concatenating in rank order needs no sort.  `state`: a GatherState shared by a sequence of calls
-    (the same on every rank); with it, short lists travel in one collective instead of two."""
+    sharding), so concatenating in rank order needs no sort."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return (local_hits if presorted else normalise_hits(local_hits)), tuple(int(x) for x in local_stats)
@@ -100,38 +86,14 @@ def gather_hits(local_hits, local_stats, group=None, dst=0, presorted=False, sta
         item = local_hits.dtype.itemsize
         hdr_np = np.array([int(local_hits.size), int(local_stats[0]), int(local_stats[1])], np.int64)
         raw = np.ascontiguousarray(local_hits).view(np.uint8).reshape(-1)
-        all_hdr = None
-        if state is not None and state.last_max is not None and state.last_max <= _FAST_CAP // 2:
-            # short lists (the previous gather of this group, whose counts every rank saw, stayed well under the cap):
-            # ONE collective -- every rank sends a fixed-size buffer [count, n_loc, n_weak | records]; every rank also
-            # receives all of them, so all ranks agree on whether a list overflowed and the general path must run
-            buf = torch.zeros(24 + _FAST_CAP * item, dtype=torch.uint8)
-            buf[:24] = torch.from_numpy(hdr_np.view(np.uint8))
-            k = min(raw.size, _FAST_CAP * item)
-            if k:
-                buf[24:24 + k] = torch.from_numpy(raw[:k])
-            bucket = [torch.empty_like(buf) for _ in range(world)]
-            dist.all_gather(bucket, buf, group=group)
-            all_hdr = [b.numpy()[:24].view(np.int64) for b in bucket]
-            counts = [int(h[0]) for h in all_hdr]
-            state.last_max = max(counts)
-            if max(counts) <= _FAST_CAP:
-                if rank != dst:
-                    return None, None
-                parts = [b.numpy()[24:24 + c * item].view(local_hits.dtype) for b, c in zip(bucket, counts)]
-                stats = (sum(int(h[1]) for h in all_hdr), sum(int(h[2]) for h in all_hdr))
-                hits = np.concatenate(parts) if parts else local_hits
-                return (hits if presorted else normalise_hits(hits)), stats
-        # general path -- host memory, two collectives, no pickling: the counts (and counters) of every rank, then the
-        # records padded to the longest list
-        if all_hdr is None:
-            hdr = torch.from_numpy(hdr_np)
-            all_t = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
-            dist.all_gather(all_t, hdr, group=group)
-            all_hdr = [t.numpy() for t in all_t]
+        # host memory, two collectives, no pickling: the counts (and counters) of every rank, then the records padded to
+        # the longest list.  (Short lists in ONE fixed-size all_gather was tried for config C: the same latency on 2 and
+        # 4 ranks, 0.4 ms slower on 8 -- gloo's ring all_gather pays per step for the payload.)
+        hdr = torch.from_numpy(hdr_np)
+        all_t = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_t, hdr, group=group)
+        all_hdr = [t.numpy() for t in all_t]
         counts = [int(h[0]) for h in all_hdr]
-        if state is not None:
-            state.last_max = max(counts)
         cap = max(max(counts), 1) * item
         buf = torch.zeros(cap, dtype=torch.uint8)
         if raw.size:
@@ -155,12 +117,10 @@ class HitGatherer:
     def __init__(self, group=None, dst=0, presorted=False):
         from concurrent.futures import ThreadPoolExecutor
         self.group, self.dst, self.presorted = group, dst, presorted
-        self.state = GatherState()
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="wbg-gather")
 
     def submit(self, local_hits, local_stats):
-        return self._pool.submit(gather_hits, local_hits, tuple(int(x) for x in local_stats), self.group, self.dst, self.presorted,
-                                 self.state)
+        return self._pool.submit(gather_hits, local_hits, tuple(int(x) for x in local_stats), self.group, self.dst, self.presorted)
 
     def close(self):
         self._pool.shutdown(wait=True)
