@@ -126,8 +126,8 @@ bool wbg_choose_cascade_geom(int m, int n, int C, CascadeGeom* g) {
             g->round_mid = env_int("WBG_CAS_ROUND_MID", 64);
             g->round_tail = env_int("WBG_CAS_ROUND_TAIL", 128);
             g->round_solo = env_int("WBG_CAS_ROUND_SOLO", 32);
-            g->round_n1 = env_int("WBG_CAS_ROUND_N1", 2 * c.threads);
-            g->round_n2 = env_int("WBG_CAS_ROUND_N2", 64);
+            g->round_n1 = env_int("WBG_CAS_ROUND_N1", 4 * c.threads);
+            g->round_n2 = env_int("WBG_CAS_ROUND_N2", 128);
             g->pack = env_int("WBG_CAS_PACK", 1);
             return true;
         }
