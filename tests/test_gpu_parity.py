@@ -659,6 +659,36 @@ def test_randomised_shapes_and_options_vs_oracle(seed):
         assert len(missing) + len(extra) + len(far) <= max(2, 0.05 * union), (len(missing), len(extra), len(far), union)
 
 
+@pytest.mark.parametrize("case", ["12x12x4 depth 2", "7x9x4 depth 3 (depth-4 records)", "12x12x4 depth 5 (node records)", "20x20x10 depth 2 (32x32 tile)",
+                                  "5x13x1 depth 1"])
+def test_many_short_rounds_vs_oracle(monkeypatch, case):
+    """The survivor pool under stress: rounds of 4-8 stages (dozens of re-packs per tile, the class-ordered pool read
+    back transposed every time, an early hand-over to the single-warp tail) for every stage encoding and tile geometry;
+    hits, scores and counters must equal the oracle's.  The round knobs are read when the model handle is created."""
+    for k, v in dict(WBG_CAS_ROUND_FULL=4, WBG_CAS_ROUND_MID=8, WBG_CAS_ROUND_TAIL=8, WBG_CAS_ROUND_SOLO=4,
+                     WBG_CAS_ROUND_N1=600, WBG_CAS_ROUND_N2=100).items():
+        monkeypatch.setenv(k, str(v))
+    shape, depth, fn = {"12x12x4 depth 2": ((12, 12, 4), 2, CH.grad_hist), "7x9x4 depth 3 (depth-4 records)": ((7, 9, 4), 3, CH.grad_hist),
+                        "12x12x4 depth 5 (node records)": ((12, 12, 4), 5, CH.grad_hist), "20x20x10 depth 2 (32x32 tile)": ((20, 20, 10), 2, CH.grad_mag_hist),
+                        "5x13x1 depth 1": ((5, 13, 1), 1, CH.grad_mag)}[case]
+    opts = dict(shrink=2, n_per_oct=3, smooth=1, channels=fn)
+    frame = S.synthetic_frame(3000 + depth, 333, 517)
+    M = make_model(shape, opts, 90, depth, frame, seed=11, keep_total=2e-3, calib_levels=2)
+    Cs = oracle_cascade(M)
+    dt = M.detect(frame)
+    got = list(M.channels(frame))
+    ref = list(Cs.channels(frame))
+    boxes, scores, _ = Cs.detect(frame)
+    assert M.n_loc == Cs.n_loc and M.n_loc > 50000
+    if all(np.array_equal(a, b) for (a, _), (b, _) in zip(got, ref)):
+        assert np.array_equal(dt.get(), boxes) and np.array_equal(dt.get_field("scores"), scores)
+        assert M.n_weak == Cs.n_weak
+    else:                                             # grad_mag channels: last-ulp differences may move single windows
+        missing, extra, moved = _hit_diff(dt.get(), dt.get_field("scores"), boxes, scores)
+        assert len(missing) + len(extra) <= 2 and abs(M.n_weak - Cs.n_weak) <= 1e-4 * Cs.n_weak, (len(missing), len(extra), M.n_weak, Cs.n_weak)
+    assert len(boxes) > 0
+
+
 def test_detect_input_edge_cases():
     """frames below the octave cut-off, non-contiguous views, unsupported dtypes (reference channels.py:93-108)."""
     frame = S.synthetic_frame(1000, 96, 128)
