@@ -13,7 +13,7 @@ from google.protobuf.message import DecodeError
 
 from . import channels as _channels
 from . import model_pb2
-from .boxes import Boxes, concatenate
+from .boxes import Boxes
 from .channels import _validate_image, resolve_channels
 from .engine import ModelHandle, get_engine
 from .training import DTree
