@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WBG_ABI_VERSION 3
+#define WBG_ABI_VERSION 4
 
 enum { WBG_OK = 0, WBG_EINVAL = -1, WBG_ECAP = -2, WBG_ECUDA = -3, WBG_ENOMEM = -4 };
 
@@ -160,6 +160,14 @@ int wbg_channel_pyramid(const wbg_plan* plan, const void* img, int32_t dtype, in
 int wbg_avg_pool_2(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream);
 int wbg_max_pool_2(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream);
 int wbg_smooth_image_3d(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream);
+/* gradients(image) (channels.py:16-21): gx = D_cols(H_rows(I)), gy = D_rows(H_cols(I)), H = [1,2,1], D = [-1,0,1]
+ * convolved ('reflect' borders, float64 accumulation, float32 per pass); img, gx, gy, tmp are [h][w] float32 on
+ * the device.  separable_convolve(image, k0, k1) (channels.py:24-27): k0 along axis 0, then k1 (k0 when NULL)
+ * along axis 1; the kernels are HOST arrays and must be symmetric with an odd length <= 63 (what the reference
+ * passes: triangle_kernel), anything else is WBG_EINVAL. */
+int wbg_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, float* tmp, void* stream);
+int wbg_separable_convolve(const float* img, int32_t h, int32_t w, const float* k0, int32_t n0, const float* k1,
+                           int32_t n1, float* out, float* tmp, void* stream);
 
 /* ---- cascade: replaces Model.predict_on_image (model.py:216-259) + DTree.predict_on_image
  * (training.py:84-96) + Model.get_boxes (model.py:136-147) over every level of every frame. */

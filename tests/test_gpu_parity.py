@@ -689,6 +689,30 @@ def test_many_short_rounds_vs_oracle(monkeypatch, case):
     assert len(boxes) > 0
 
 
+def test_public_gradients_and_separable_convolve_vs_oracle():
+    """channels.gradients / separable_convolve as public functions (reference channels.py:16-27), bit for bit against
+    the oracle (itself pinned against scipy in tests/test_oracle_pins.py): odd sizes, images shorter than the kernel
+    (repeated reflection), the triangle kernels grad_mag uses, two different kernels, empty images."""
+    rng = np.random.default_rng(5)
+    for h, w in [(37, 53), (1, 9), (8, 1), (3, 4), (2, 2), (64, 96)]:
+        img = (rng.random((h, w)) * 255).astype(np.float32)
+        gx, gy = CH.gradients(img)
+        ox, oy = O.gradients(img)
+        assert gx.dtype == np.float32 and np.array_equal(gx, ox) and np.array_equal(gy, oy), (h, w)
+        for norm in (1, 2, 5, 8):
+            k = CH.triangle_kernel(norm)
+            assert np.array_equal(CH.separable_convolve(img, k), O.separable_convolve(img, k)), (h, w, norm)
+    img = (rng.random((21, 34)) * 255).astype(np.float32)
+    k0, k1 = CH.triangle_kernel(3), np.array([1, 2, 1], np.float32)
+    ref = O._correlate1d_sym(O._correlate1d_sym(img, k0, 0), k1, 1)
+    assert np.array_equal(CH.separable_convolve(img, k0, k1), ref)
+    assert CH.gradients(np.zeros((0, 5), np.float32))[0].shape == (0, 5)
+    with pytest.raises(ValueError):
+        CH.separable_convolve(img, np.array([1, 2, 3], np.float32))        # not symmetric
+    with pytest.raises(TypeError):
+        CH.gradients(img.astype(np.float64))
+
+
 def test_detect_input_edge_cases():
     """frames below the octave cut-off, non-contiguous views, unsupported dtypes (reference channels.py:93-108)."""
     frame = S.synthetic_frame(1000, 96, 128)

@@ -12,7 +12,7 @@ WBG_OK, WBG_EINVAL, WBG_ECAP, WBG_ECUDA, WBG_ENOMEM = 0, -1, -2, -3, -4
 WBG_U8, WBG_F32 = 0, 1
 WBG_CH_GRAD_HIST, WBG_CH_GRAD_MAG, WBG_CH_GRAD_MAG_HIST, WBG_CH_FPGA_HIST4_U1, WBG_CH_FPGA_MAG_U1 = 0, 1, 2, 3, 4
 WBG_MAX_BINS, WBG_MAX_NORM, WBG_MAX_CHANNELS = 16, 8, 17
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ChannelOpts(C.Structure):
@@ -65,6 +65,8 @@ SYMBOLS = {
     "wbg_avg_pool_2": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "wbg_max_pool_2": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "wbg_smooth_image_3d": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "wbg_gradients": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P]),
+    "wbg_separable_convolve": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _P]),
     "wbg_model_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),
     "wbg_model_destroy": (None, [_P]),
     "wbg_cascade_workspace_bytes": (_SZ, [_P, _I32]),

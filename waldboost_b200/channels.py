@@ -12,13 +12,39 @@ import numpy as np
 from . import _native as N
 
 __all__ = ["grad_hist", "grad_mag", "grad_mag_hist", "channel_pyramid", "avg_pool_2", "max_pool_2",
-           "smooth_image_3d", "triangle_kernel", "resolve_channels"]
+           "smooth_image_3d", "triangle_kernel", "gradients", "separable_convolve", "resolve_channels"]
 
 
 def triangle_kernel(n):
     """reference channels.py:11-13."""
     H = (np.r_[:n + 1, n - 1:-1:-1] + 1).astype("f")
     return H / H.sum()
+
+
+def _image_f32(image, what):
+    a = np.asarray(image)
+    if a.ndim != 2 or a.dtype != np.float32:
+        raise TypeError(f"{what} on the GPU takes a 2-D float32 image")
+    return a
+
+
+def gradients(image):
+    """(gx, gy) = negated Sobel gradients: H = [1,2,1] along one axis, D = [-1,0,1] convolved along the other, 'reflect'
+    borders (reference channels.py:16-21); 2-D float32 image -> two float32 arrays."""
+    from .engine import get_engine
+    return get_engine().gradients(_image_f32(image, "gradients"))
+
+
+def separable_convolve(image, k0, k1=None):
+    """convolve1d(image, k0, axis=0) followed by convolve1d(., k1 or k0, axis=1) (reference channels.py:24-27).  The
+    kernels must be symmetric with an odd length <= 63 -- what the reference itself passes (triangle_kernel); other
+    kernels take a different accumulation order in scipy and are rejected (ValueError)."""
+    from .engine import get_engine
+    for k in (k0,) if k1 is None else (k0, k1):
+        k = np.asarray(k, np.float32)
+        if k.ndim != 1 or k.size % 2 == 0 or k.size > 63 or not np.array_equal(k, k[::-1]):
+            raise ValueError("separable_convolve on the GPU takes symmetric 1-D kernels of odd length <= 63")
+    return get_engine().separable_convolve(_image_f32(image, "separable_convolve"), k0, k1)
 
 
 # ----------------------------------------------------------------------------------------------- channel functions

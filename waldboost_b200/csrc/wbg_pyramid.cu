@@ -1481,6 +1481,81 @@ extern "C" int wbg_max_pool_2(const float* in, int32_t u, int32_t v, int32_t c, 
     return WBG_OK;
 }
 
+// ---- public single-image forms of the gradient helpers (channels.py:16-27), float32 images.  scipy's convolve1d in
+// 'reflect' mode: float64 accumulation per output, one rounding to float32 per pass; symmetric kernels accumulate the
+// centre tap first and then the pairs from the outermost inwards (NI_Correlate1D's symmetric branch).
+struct SymKernel { int half; float w[64]; };       // w[0..2*half], odd length, w[i] == w[2*half - i]
+
+__global__ void sym_conv_kernel(const float* __restrict__ in, int h, int w, int axis, SymKernel k, float* __restrict__ out) {
+    const long long total = (long long)h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        const int n = axis == 0 ? h : w, l = axis == 0 ? y : x;
+        const long long stride = axis == 0 ? w : 1;
+        const float* __restrict__ line = in + (axis == 0 ? x : (long long)y * w);
+        double acc = (double)line[l * stride] * (double)k.w[k.half];
+        for (int d = -k.half; d < 0; ++d)
+            acc += ((double)line[reflect_idx(l + d, n) * stride] + (double)line[reflect_idx(l - d, n) * stride]) * (double)k.w[k.half + d];
+        out[i] = (float)acc;
+    }
+}
+
+// convolve1d(x, [-1, 0, 1], axis): the convolution flips the kernel, so the result is x[l-1] - x[l+1] (anti-symmetric branch)
+__global__ void diff_conv_kernel(const float* __restrict__ in, int h, int w, int axis, float* __restrict__ out) {
+    const long long total = (long long)h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        const int n = axis == 0 ? h : w, l = axis == 0 ? y : x;
+        const long long stride = axis == 0 ? w : 1;
+        const float* __restrict__ line = in + (axis == 0 ? x : (long long)y * w);
+        const double acc = (double)line[l * stride] * 0.0 + ((double)line[reflect_idx(l - 1, n) * stride] - (double)line[reflect_idx(l + 1, n) * stride]) * 1.0;
+        out[i] = (float)acc;
+    }
+}
+
+static bool make_sym_kernel(const float* k, int n, SymKernel* out) {
+    if (!k || n < 1 || n > 63 || (n & 1) == 0) return false;
+    for (int i = 0; i < n / 2; ++i)
+        if (memcmp(k + i, k + n - 1 - i, sizeof(float)) != 0) return false;
+    out->half = n / 2;
+    memcpy(out->w, k, sizeof(float) * (size_t)n);
+    return true;
+}
+
+extern "C" int wbg_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, float* tmp, void* stream) {
+    WBG_REQUIRE(h >= 0 && w >= 0, "wbg_gradients: bad sizes");
+    if ((long long)h * w == 0) return WBG_OK;
+    WBG_REQUIRE(img && gx && gy && tmp, "wbg_gradients: null argument");
+    const float h121[3] = {1.f, 2.f, 1.f};
+    SymKernel k;
+    make_sym_kernel(h121, 3, &k);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for((long long)h * w);
+    sym_conv_kernel<<<grid, 256, 0, st>>>(img, h, w, 1, k, tmp);      // gy = D_rows(H_cols(I))   (channels.py:19)
+    diff_conv_kernel<<<grid, 256, 0, st>>>(tmp, h, w, 0, gy);
+    sym_conv_kernel<<<grid, 256, 0, st>>>(img, h, w, 0, k, tmp);      // gx = D_cols(H_rows(I))   (channels.py:20)
+    diff_conv_kernel<<<grid, 256, 0, st>>>(tmp, h, w, 1, gx);
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
+extern "C" int wbg_separable_convolve(const float* img, int32_t h, int32_t w, const float* k0, int32_t n0, const float* k1,
+                                      int32_t n1, float* out, float* tmp, void* stream) {
+    WBG_REQUIRE(h >= 0 && w >= 0, "wbg_separable_convolve: bad sizes");
+    SymKernel a, b;
+    WBG_REQUIRE(make_sym_kernel(k0, n0, &a), "wbg_separable_convolve: k0 must be a symmetric kernel of odd length <= 63");
+    if (k1) WBG_REQUIRE(make_sym_kernel(k1, n1, &b), "wbg_separable_convolve: k1 must be a symmetric kernel of odd length <= 63");
+    else b = a;
+    if ((long long)h * w == 0) return WBG_OK;
+    WBG_REQUIRE(img && out && tmp, "wbg_separable_convolve: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for((long long)h * w);
+    sym_conv_kernel<<<grid, 256, 0, st>>>(img, h, w, 0, a, tmp);      // channels.py:25
+    sym_conv_kernel<<<grid, 256, 0, st>>>(tmp, h, w, 1, b, out);      // channels.py:26 (in place in the reference)
+    WBG_CUDA_TRY(cudaGetLastError());
+    return WBG_OK;
+}
+
 extern "C" int wbg_smooth_image_3d(const float* in, int32_t u, int32_t v, int32_t c, float* out, void* stream) {
     WBG_REQUIRE(u >= 0 && v >= 0 && c >= 1, "wbg_smooth_image_3d: bad sizes");
     if ((long long)u * v == 0) return WBG_OK;

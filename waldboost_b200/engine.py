@@ -522,6 +522,33 @@ class Engine:
         N.check(self.lib.wbg_profile_read(ms, n))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(N.PROF_KINDS)}
 
+    def gradients(self, image):
+        """(gx, gy) of a 2-D float32 image (reference channels.py:16-21)."""
+        torch = self.torch
+        h, w = image.shape
+        Xd = torch.from_numpy(np.ascontiguousarray(image, np.float32)).to(self.device)
+        buf = torch.zeros((3, max(h * w, 1)), dtype=torch.float32, device=self.device)        # gx | gy | scratch
+        if h * w:
+            with torch.cuda.device(self.device):
+                N.check(self.lib.wbg_gradients(C.c_void_p(Xd.data_ptr()), h, w, C.c_void_p(buf[0].data_ptr()),
+                                               C.c_void_p(buf[1].data_ptr()), C.c_void_p(buf[2].data_ptr()), self._stream()))
+        host = buf[:2, :h * w].cpu().numpy()
+        return host[0].reshape(h, w), host[1].reshape(h, w)
+
+    def separable_convolve(self, image, k0, k1=None):
+        """k0 along axis 0, then k1 (default k0) along axis 1 (reference channels.py:24-27); symmetric odd kernels."""
+        torch = self.torch
+        h, w = image.shape
+        Xd = torch.from_numpy(np.ascontiguousarray(image, np.float32)).to(self.device)
+        buf = torch.zeros((2, max(h * w, 1)), dtype=torch.float32, device=self.device)        # out | scratch
+        k0 = np.ascontiguousarray(k0, np.float32)
+        k1 = None if k1 is None else np.ascontiguousarray(k1, np.float32)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.wbg_separable_convolve(C.c_void_p(Xd.data_ptr()), h, w, k0.ctypes.data_as(C.c_void_p), int(k0.size),
+                                                    None if k1 is None else k1.ctypes.data_as(C.c_void_p), 0 if k1 is None else int(k1.size),
+                                                    C.c_void_p(buf[0].data_ptr()), C.c_void_p(buf[1].data_ptr()), self._stream()))
+        return buf[0, :h * w].cpu().numpy().reshape(h, w)
+
     def map_primitive(self, fn_name, arr, out_shape):
         torch = self.torch
         a3 = arr.reshape(arr.shape[0], arr.shape[1], -1)
