@@ -488,6 +488,72 @@ def run_config_c(args):
         dist.destroy_process_group()
 
 
+def run_config_small(args):
+    """BASELINE configs[0] (A: one 640x480 frame through Model.detect, the reference's own CPU-runnable case) and
+    configs[3] (D: dense scoring of 1000 640x480 images with a 2048-stage depth-4 cascade, the Pool.update pattern), one
+    GPU, through the public API with host buffers.  Both use the committed reference-written models and compare a
+    result with the reference's own output before timing (tests/golden/configA_detect.npz, configD_scan.npz)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                              # single-GPU configurations: other ranks have nothing to do
+    import waldboost_b200 as wb
+    from waldboost_b200 import synthetic as S
+    golden = os.path.join(ROOT, "tests", "golden")
+    if args.config == "A":
+        M = wb.Model.load(os.path.join(golden, "configA_model.pb"))
+        g = np.load(os.path.join(golden, "configA_detect.npz"))
+        frame = S.synthetic_frame(1000, 480, 640)
+        M.reset()
+        dt = M.detect(frame)
+        same = bool(np.array_equal(dt.get(), g["boxes"]) and np.array_equal(dt.get_field("scores"), g["scores"])
+                    and (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"])))
+        run, units, what = (lambda: M.detect(frame)), 1, "640x480 frames/sec for Model.detect, one frame at a time (latency)"
+        workload = "one 640x480 uint8 frame per step, 12x12x4 grad_hist model, 256 depth-2 stages, wald thetas (BASELINE configs[0])"
+        h2d, extra = frame.nbytes, {"hits": len(dt), "eval_cost": M.eval_cost}
+    else:
+        M = wb.Model.load(os.path.join(golden, "configD_model.pb"))
+        g = np.load(os.path.join(golden, "configD_scan.npz"))
+        small = S.synthetic_frame(1003, 200, 260)
+        M.reset()
+        got = [h for _, _, (_, _, h) in M.scan_channels(small)]
+        same = bool(len(got) == int(g["n_levels"]) and all(np.array_equal(h, g[f"{k}/h"]) for k, h in enumerate(got))
+                    and (M.n_loc, M.n_weak) == (int(g["n_loc"]), int(g["n_weak"])))
+        base = [S.synthetic_frame(1000 + i, 480, 640) for i in range(16)]
+        pinned = torch.empty((1000, 480, 640), dtype=torch.uint8, pin_memory=True)
+        frames = pinned.numpy()
+        for i in range(1000):
+            frames[i] = base[i % 16]
+        M.reset()
+        run, units, what = (lambda: M.detect_batch(frames, return_hits=True)), 1000, "640x480 images/sec, dense scoring with a 2048-stage depth-4 cascade"
+        workload = ("1000 synthetic 640x480 uint8 images per step (16 distinct ones cycled), 12x12x4 grad_hist model, 2048 depth-4 stages, "
+                    "wald thetas (BASELINE configs[3]); every image's surviving windows and scores come back to the host")
+        h2d, extra = frames.nbytes, {}
+    for _ in range(max(args.warmup, 3)):
+        out = run()
+    torch.cuda.synchronize()
+    steps = args.steps if args.config == "D" else max(args.steps, 50)
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = run()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+    if args.config == "D":
+        extra = {"hits_per_image": out[1].size / 1000.0, "eval_cost": M.eval_cost}
+    line = {"metric": what, "value": units * steps / dt_s, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dt_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": dict({"workload": workload, "matches_reference_golden": same,
+                            "timed_region": "public API per step: host frames in (H2D inside), boxes / hit records out (D2H inside)"}, **extra),
+            "e2e": {"value": units * steps / dt_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": None},
+            "gpu_launches": None, "clocks": clk.summary()}
+    print(json.dumps(line), flush=True)
+    if not same:
+        raise SystemExit(f"config {args.config}: the result differs from the reference golden")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -502,11 +568,14 @@ def main():
     ap.add_argument("--no-single-thread", action="store_true", help="skip the single-core sample of the CPU arm")
     ap.add_argument("--cpu-kind", choices=["auto", "port", "reference"], default="auto",
                     help="CPU arm: the unmodified reference (needs /root/reference), its NumPy restatement, or whichever is available")
-    ap.add_argument("--config", choices=["B", "C"], default="B", help="B: batch of 1080p frames (default, the headline); "
-                    "C: one 3840x2160 frame spread over the GPUs in row bands")
+    ap.add_argument("--config", choices=["A", "B", "C", "D"], default="B", help="B: batch of 1080p frames (default, the headline); "
+                    "C: one 3840x2160 frame spread over the GPUs in row bands; A: one 640x480 frame (latency); "
+                    "D: dense scoring of 1000 640x480 images with a 2048-stage depth-4 cascade")
     args = ap.parse_args()
     if args.config == "C" and args.impl != "reference":
         return run_config_c(args)
+    if args.config in ("A", "D") and args.impl != "reference":
+        return run_config_small(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -41,6 +41,16 @@ def test_gpu_arm_prints_one_json_line():
     assert d["config"]["windows_per_frame"] == 3045278 and d["config"]["levels"] == 64
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", ["A", "D"])
+def test_small_configs_print_one_json_line_and_match_their_golden(config):
+    """bench.py --config A / D: BASELINE configs[0] and configs[3], each compared with the reference's own output
+    (tests/golden/) inside the run."""
+    d = _run(["--config", config, "--steps", "2", "--warmup", "3"], 900)
+    assert (BASE_KEYS - {"cpu_baseline"}) <= set(d) and d["value"] > 0 and d["unit"] == "frames/s"
+    assert d["config"]["matches_reference_golden"] is True and d["config"]["eval_cost"] > 1
+
+
 def test_cpu_arm_inputs_match_the_product_side():
     """oracle/cpu_arm.py restates the frame recipe and parses the model file on its own (it never imports the product):
     both must give what the GPU arm uses."""
